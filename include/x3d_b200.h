@@ -1,0 +1,132 @@
+/*
+ * x3d_b200.h -- C ABI of the B200 (sm_100a) X3D forward path.
+ *
+ * The reference (fcogidi/X3D-tf) has no FFI of its own: its hot path is a chain of
+ * tf.keras layer calls inside model.py.  Each entry point below replaces the TensorFlow op
+ * (or short chain of ops) that one of those call sites lowers to; the reference call site is
+ * cited on every function.  The Python classes in x3d_tf_b200/model.py (same names and
+ * constructor arguments as model.py) bind these through ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - Plain C: device pointers, sizes, a cudaStream_t passed as void*.  No torch types.
+ *   - Every call is asynchronous on `stream`, never synchronises, never allocates.
+ *   - Return value: 0 = ok, negative = X3D_ERR_*.  x3d_last_error() gives a thread-local text.
+ *   - Activations are channels-last NDHWC, row-major, `C` = STORED channel count, which must be a
+ *     multiple of 8 (the host zero-pads 54->56, 108->112 ...; padded channels carry zeros and
+ *     have zero weights).  The stem's 3-channel input is the only exception.
+ *   - `dtype` selects the storage type of activations: X3D_F32 or X3D_BF16.  Arithmetic is
+ *     fp32-accumulate in both cases.  Weights/biases passed as `const float*` are fp32 with the
+ *     inference BatchNorm already folded in (scale into the kernel, shift as bias).
+ *   - 64-bit element offsets are used throughout (X3D-L activations exceed 2^31 bytes).
+ */
+#ifndef X3D_B200_H_
+#define X3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define X3D_B200_VERSION 100
+
+enum x3d_dtype { X3D_F32 = 0, X3D_BF16 = 1 };
+
+enum x3d_status {
+  X3D_OK = 0,
+  X3D_ERR_INVALID_ARG = -1,   /* bad size / alignment / dtype / null pointer */
+  X3D_ERR_UNSUPPORTED = -2,   /* shape outside what the kernel was built for */
+  X3D_ERR_LAUNCH = -3,        /* CUDA reported an error at launch */
+  X3D_ERR_NO_DEVICE = -4      /* no sm_100 device / driver entry point missing */
+};
+
+int x3d_version(void);
+const char* x3d_last_error(void);
+
+/* CRC-32C (Castagnoli) of a host buffer, continuing from `crc` (0 to start).  Used by the
+ * TF-bundle reader that stands in for model.load_weights (train.py:137-143, eval.py:78-81). */
+uint32_t x3d_crc32c(const void* data, size_t len, uint32_t crc);
+
+/* ---- Stem: X3D_Stem.call, model.py:202-210 -------------------------------------------------
+ * tf.pad(H,W by 1) -> Conv3D 1x3x3 s(1,2,2) valid -> tf.pad(T by kt/2) -> channelwise Conv3D
+ * kt x1x1 -> BatchNormalization -> ReLU, as ONE kernel.
+ *   in   [N,T,H,W,3]        in_dtype (X3D_F32 | X3D_BF16)
+ *   ws   [3,3,3,C] fp32     conv_s kernel (dh,dw,ci,c)
+ *   wt   [kt,C]   fp32      conv_t kernel with the BN scale folded in
+ *   bias [C]      fp32      BN shift
+ *   out  [N,T,Ho,Wo,C]      out_dtype;  Ho=(H-1)/2+1, Wo=(W-1)/2+1
+ * kt must be 5 (NETWORK.C1_TEMP_FILTER of every shipped config). */
+int x3d_stem_fwd(const void* in, int in_dtype, const float* ws, const float* wt,
+                 const float* bias, void* out, int out_dtype,
+                 int N, int T, int H, int W, int C, int kt, void* stream);
+
+/* ---- Pointwise (1x1x1) convolution as a GEMM, SIMT fp32-accumulate path ---------------------
+ * One entry point for Bottleneck.a+bn_a+relu (model.py:306-308), Bottleneck.c+bn_c with the
+ * SE-scale/swish prologue and the residual add + ReLU of ResBlock (model.py:311-318,389-392),
+ * the strided shortcut conv + bn_r (model.py:386-388), conv5 (model.py:117) and the head's
+ * fc1 / fc2 (model.py:119-121).
+ *   D[m, 0:Nc] = act( bias + sum_k pro(A[row(m), k]) * Wt[k, 0:Nc] (+ R[m, 0:Nc]) )
+ *   A    [*, lda]   a_dtype;  row(m) = m, or for gather != 0 the input pixel
+ *                   (n, t, ho*stride, wo*stride) of output pixel m = ((n*T+t)*Ho+ho)*Wo+wo
+ *   Wt   [K, ldw]   fp32, BN scale folded;  bias [Nc] fp32 (may be NULL)
+ *   pro(a) = a                         if se == NULL and !swish
+ *          = swish(a * se[m / rows_per_clip, k])   (se NULL => factor 1; swish(x)=x*sigmoid(x))
+ *   R    [M, ldr]   residual, d_dtype (may be NULL);  act = ReLU if relu else identity
+ *   D    [M, ldd]   d_dtype */
+typedef struct x3d_pw_args {
+  const void* A; const float* Wt; const float* bias; const void* R; const float* se; void* D;
+  int64_t M; int32_t K, Nc, lda, ldw, ldr, ldd;
+  int64_t rows_per_clip;
+  int32_t a_dtype, d_dtype, swish, relu;
+  int32_t gather, T, Ho, Wo, Hi, Wi, stride;
+} x3d_pw_args;
+int x3d_pw_fwd(const x3d_pw_args* args, void* stream);
+
+/* ---- Channelwise 3x3x3 convolution: Bottleneck.b + bn_b, model.py:309-310 -------------------
+ * Grouped Conv3D(groups=C) stride (1,s,s), TF padding='same' (T: 1 before; H/W: pad_h/pad_w
+ * before, derived on the host from TF's rule), + BN, and -- when `se_partial` != NULL -- the
+ * per-clip, per-channel sums of the output that se_pool (model.py:312) needs, written as
+ * fixed-order partial sums (deterministic; no atomics):
+ *   in  [N,T,H,W,C]; w [27,C] fp32 (dt,dh,dw major; BN scale folded); bias [C] fp32
+ *   out [N,T,Ho,Wo,C], Ho=ceil(H/s), Wo=ceil(W/s)
+ *   se_partial [N, nblk, C] fp32 with nblk = x3d_dw_partial_blocks(...) */
+int x3d_dw_partial_blocks(int T, int H, int W, int C, int stride);
+int x3d_dw3x3x3_fwd(const void* in, const float* w, const float* bias, void* out,
+                    float* se_partial, int N, int T, int H, int W, int C, int stride,
+                    int pad_h, int pad_w, int dtype, void* stream);
+
+/* ---- Squeeze-Excitation MLP: se_pool/se_fc1/se_fc2, model.py:311-314 ------------------------
+ *   mean[n,c] = inv_count * sum_b partial[n,b,c];  z = relu(mean.w1 + b1);  scale = sigmoid(z.w2 + b2)
+ *   w1 [C,Cw], b1 [Cw], w2 [Cw,C], b2 [C] fp32;  scale [N,C] fp32.   Cw <= 64. */
+int x3d_se_mlp_fwd(const float* partial, int nblk, float inv_count, const float* w1,
+                   const float* b1, const float* w2, const float* b2, float* scale,
+                   int N, int C, int Cw, void* stream);
+
+/* ---- Global average pool: AdaptiveAvgPool3D.call, model.py:473-483 --------------------------
+ *   in [N,P,C] dtype -> out [N,C] fp32 (mean over the P = T*H*W positions), fixed order. */
+int x3d_avgpool_fwd(const void* in, float* out, int N, int64_t P, int C, int dtype, void* stream);
+
+/* ---- Softmax (fp32) + view average: model.py:122-127 ----------------------------------------
+ *   logits [N,ncls] fp32 -> probs [N/num_preds, ncls] fp32; num_preds consecutive rows are one
+ *   video (dataloader.py:107-116).  num_preds = 1 gives the training-mode output. */
+int x3d_softmax_viewmean_fwd(const float* logits, float* probs, int N, int ncls, int num_preds,
+                             void* stream);
+
+/* ---- Pointwise convolution on the 5th-gen tensor cores (bf16 in, fp32 accumulate in TMEM) ----
+ * Same contract as x3d_pw_fwd for a_dtype = d_dtype = X3D_BF16 and gather == 0, but the weights
+ * are pre-packed bf16: Wp [Npad, Kpad] (K contiguous), Npad % 16 == 0, Kpad % 64 == 0, zero
+ * padded, BN scale folded.  A tiles arrive by TMA (128B swizzle), tcgen05.mma accumulates in
+ * TMEM, the epilogue adds bias (+ residual), applies ReLU and stores bf16. */
+typedef struct x3d_pw_tc_args {
+  const void* A; const void* Wp; const float* bias; const void* R; const float* se; void* D;
+  int64_t M; int32_t K, Nc, lda, ldr, ldd, Kpad, Npad;
+  int64_t rows_per_clip;
+  int32_t swish, relu;
+} x3d_pw_tc_args;
+int x3d_pw_tc_fwd(const x3d_pw_tc_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* X3D_B200_H_ */

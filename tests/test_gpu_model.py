@@ -1,0 +1,162 @@
+"""Block-level and whole-model parity of the CUDA path against the CPU oracle, plus
+size-independent properties at larger shapes (tiers 3 and 5)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import x3d_oracle as O
+from tests.gpu_util import assert_close, bf16_round, dev, rel_err, to_dev, to_np
+from x3d_tf_b200.arch import build_arch
+from x3d_tf_b200.config import get_config
+from x3d_tf_b200.synth import synthetic_clips, synthetic_weights
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4       # north_star: fp32 logits within 1e-4 relative
+BF16_TOL = 2e-2       # north_star: bf16 logits within 2e-2 relative, identical top-1
+
+
+def _model(variant, dtype=None, views=None, seed=1111, graph=False):
+    from x3d_tf_b200 import model as M
+    M.reset_block_counters()
+    cfg = get_config(variant, freeze=False)
+    if views is not None:
+        cfg.TEST.NUM_TEMPORAL_VIEWS, cfg.TEST.NUM_SPATIAL_CROPS = views, 1
+    cfg.freeze()
+    m = M.X3D(cfg, dtype=dtype, use_cuda_graph=graph)
+    W = synthetic_weights(build_arch(cfg), seed=seed)
+    m.set_weights_dict(W)
+    return m, cfg, W, O.OracleSpec.from_cfg(cfg)
+
+
+def _check_logits(got, want, tol, check_top1):
+    err = rel_err(got, want)
+    assert err < tol, f"relative logit error {err:.3e} >= {tol}"
+    if check_top1:
+        # identical top-1 wherever the oracle's own margin is resolvable at this error level
+        srt = np.sort(want, -1)
+        margin = srt[:, -1] - srt[:, -2]
+        decided = margin > 2 * np.abs(got - want).max()
+        assert decided.any()
+        assert (got.argmax(-1)[decided] == want.argmax(-1)[decided]).all()
+    return err
+
+
+@pytest.mark.parametrize("variant,shape", [("X3D_XS", (4, 4, 64, 64)), ("X3D_XS", (2, 4, 91, 75)),
+                                           ("X3D_M", (2, 8, 64, 64))])
+def test_whole_model_fp32(variant, shape):
+    m, cfg, W, spec = _model(variant, views=2)
+    x = synthetic_clips(*shape, cfg.DATA.MEAN, cfg.DATA.STD, seed=3)
+    want = O.forward(W, spec, x, torch.float64)
+    probs = m(to_dev(x))
+    _check_logits(to_np(m.last_logits), want["logits"], FP32_TOL, True)
+    np.testing.assert_allclose(to_np(probs), want["probs"], rtol=1e-3, atol=1e-7)
+    assert probs.shape == (shape[0] // 2, 400)
+
+
+@pytest.mark.parametrize("pointwise", ["tc", "simt"])
+@pytest.mark.parametrize("variant,shape", [("X3D_XS", (4, 4, 64, 64)), ("X3D_S", (2, 13, 91, 91)),
+                                           ("X3D_M", (2, 16, 64, 64))])
+def test_whole_model_bf16(variant, shape, pointwise):
+    from x3d_tf_b200 import model as M
+    M.Options.pointwise = pointwise
+    try:
+        m, cfg, W, spec = _model(variant, dtype="bfloat16", views=1)
+        x = synthetic_clips(*shape, cfg.DATA.MEAN, cfg.DATA.STD, seed=4)
+        want = O.forward(W, spec, x, torch.float64)
+        m(to_dev(x))                                   # fp32 clips read directly by the stem
+        e1 = _check_logits(to_np(m.last_logits), want["logits"], BF16_TOL, True)
+        m(to_dev(x, torch.bfloat16))                   # bf16 clips (BASELINE config 2)
+        want_b = O.forward(W, spec, bf16_round(x), torch.float64)
+        _check_logits(to_np(m.last_logits), want_b["logits"], BF16_TOL, True)
+        print(f"{variant} {shape} {pointwise}: bf16 rel logit err {e1:.2e}")
+    finally:
+        M.Options.pointwise = "tc"
+
+
+def test_large_variants_build_and_run_bf16():
+    """X3D-L / XL graphs (55 blocks, SE on flipped parity, 630-wide stage) at a tiny input."""
+    for variant in ("X3D_L", "X3D_XL"):
+        m, cfg, W, spec = _model(variant, dtype="bfloat16", views=1)
+        x = synthetic_clips(1, 4, 45, 39, cfg.DATA.MEAN, cfg.DATA.STD, seed=5)
+        want = O.forward(W, spec, x, torch.float64)
+        m(to_dev(x))
+        _check_logits(to_np(m.last_logits), want["logits"], BF16_TOL, False)
+
+
+def test_blocks_standalone_api():
+    """Reference class API: ResStage / ResBlock / Bottleneck / X3D_Stem / AdaptiveAvgPool3D."""
+    from x3d_tf_b200 import model as M
+    M.reset_block_counters()
+    cfg = get_config("X3D_M")
+    rng = np.random.default_rng(0)
+    # ResStage(24 -> 54 -> 24, depth 3): blocks 1..3, SE on 1 and 3; stride-2 shortcut on the first
+    st = M.ResStage(in_channels=24, inner_channels=54, out_channels=24, depth=3, bn_cfg=cfg.NETWORK.BN)
+    assert st._inner_channels == 54 and [b.bottleneck.has_se for b in st.blocks] == [True, False, True]
+    arch = build_arch(cfg)
+    W = synthetic_weights(arch, seed=9)
+    st.set_weights_dict(W, prefix="stages/0/")
+    x = rng.normal(size=(2, 4, 15, 18, 24)).astype(np.float32)
+    spec = O.OracleSpec.from_cfg(cfg)
+    ref = torch.from_numpy(x).double().permute(0, 4, 1, 2, 3)
+    for blk in spec.blocks[:3]:
+        ref = O.res_block(W, ref, blk, spec, torch.float64)
+    got = st(to_dev(x))
+    assert got.shape == (2, 4, 8, 9, 24)
+    assert_close(to_np(got), O.to_ndhwc(ref), torch.float32, "ResStage")
+    # Bottleneck alone (no residual, no final ReLU)
+    bt = st.blocks[1].bottleneck
+    y = rng.normal(size=(1, 3, 6, 5, 24)).astype(np.float32)
+    refb = O.bottleneck(W, torch.from_numpy(y).double().permute(0, 4, 1, 2, 3),
+                        "stages/0/stage/layer_with_weights-1", 54, 1, 0, spec, torch.float64)
+    assert_close(to_np(bt(to_dev(y))), O.to_ndhwc(refb), torch.float32, "Bottleneck")
+    # pool
+    p = M.AdaptiveAvgPool3D((1, 1, 1))(to_dev(y))
+    assert p.shape == (1, 1, 1, 1, 24)
+    np.testing.assert_allclose(to_np(p).ravel(), y.mean((0, 1, 2, 3)), rtol=1e-5, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        st(to_dev(x), training=True)
+
+
+def test_determinism_batch_independence_and_graph_replay():
+    """Properties that do not need the oracle: bit-exact reruns, a clip's logits do not depend on
+    its batch neighbours (inference BN, per-clip SE), CUDA-graph replay == eager launches."""
+    m, cfg, W, spec = _model("X3D_M", dtype="bfloat16", views=1)
+    x = to_dev(synthetic_clips(6, 16, 112, 112, cfg.DATA.MEAN, cfg.DATA.STD, seed=8), torch.bfloat16)
+    m(x)
+    l1 = m.last_logits.clone()
+    m(x)
+    assert torch.equal(l1, m.last_logits)
+    m(x[2:4].contiguous())
+    assert torch.equal(l1[2:4], m.last_logits)
+    mg, *_ = _model("X3D_M", dtype="bfloat16", views=1, graph=True)
+    for _ in range(3):
+        mg(x)
+    assert torch.equal(l1, mg.last_logits)
+    # view averaging: 3 views of the same clip average to that clip's softmax
+    m3, *_ = _model("X3D_M", dtype="bfloat16", views=3)
+    p3 = m3(x)
+    p1 = torch.softmax(l1.float(), -1).reshape(2, 3, -1).mean(1)
+    np.testing.assert_allclose(to_np(p3), to_np(p1), rtol=1e-4, atol=1e-8)
+    with pytest.raises(ValueError):
+        m3(x[:4])
+
+
+def test_checkpoint_round_trip(tmp_path):
+    """save -> TF-bundle on disk -> load_weights(...).expect_partial() -> identical logits."""
+    m, cfg, W, _ = _model("X3D_XS", views=1)
+    x = to_dev(synthetic_clips(1, 4, 48, 48, cfg.DATA.MEAN, cfg.DATA.STD, seed=2))
+    m(x)
+    l1 = m.last_logits.clone()
+    prefix = str(tmp_path / "ckpt" / "model")
+    W2 = dict(W)
+    W2["optimizer/iter"] = np.array(7, np.int64)
+    from x3d_tf_b200 import tf_bundle
+    tf_bundle.write_bundle(prefix, W2)
+    m2, *_ = _model("X3D_XS", views=1, seed=999)
+    m2(x)
+    assert not torch.equal(l1, m2.last_logits)
+    status = m2.load_weights(tf_bundle.latest_checkpoint(str(tmp_path / "ckpt")))
+    status.expect_partial().assert_existing_objects_matched()
+    m2(x)
+    assert torch.equal(l1, m2.last_logits)

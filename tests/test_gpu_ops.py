@@ -1,0 +1,241 @@
+"""Per-kernel parity of the CUDA path (through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_ops
+from oracle import x3d_oracle as O
+from tests.gpu_util import (assert_close, bf16_round, dev, ncdhw64, rel_err, to_dev, to_np)
+
+pytestmark = pytest.mark.gpu
+DT = [torch.float32, torch.bfloat16]
+
+
+def _ops():
+    from x3d_tf_b200 import ops
+    return ops
+
+
+def _q(a, dtype):
+    return bf16_round(a) if dtype == torch.bfloat16 else np.asarray(a, np.float32)
+
+
+# ------------------------------------------------------------------------------- stem
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("N,T,H,W,C", [(2, 4, 32, 32, 24), (1, 5, 37, 45, 24), (1, 13, 18, 50, 32),
+                                       (2, 1, 8, 8, 24), (1, 3, 33, 31, 40)])
+def test_stem(dtype, N, T, H, W, C):
+    rng = np.random.default_rng(N * 1000 + H)
+    x = _q(rng.normal(size=(N, T, H, W, 3)), dtype)
+    ks = rng.normal(size=(1, 3, 3, 3, C)).astype(np.float32) * 0.3
+    kt = rng.normal(size=(5, 1, 1, 1, C)).astype(np.float32) * 0.5
+    bias = rng.normal(size=C).astype(np.float32) * 0.2
+    want = np.maximum(np_ops.stem_convs(x, ks, kt) + bias, 0.0)
+    got = _ops().stem_fwd(to_dev(x, dtype), to_dev(ks.reshape(27, C)), to_dev(kt.reshape(5, C)),
+                          to_dev(bias), dtype)
+    assert_close(to_np(got), want, dtype, "stem")
+
+
+def test_stem_mixed_dtypes():
+    rng = np.random.default_rng(7)
+    x = rng.normal(size=(1, 4, 20, 20, 3)).astype(np.float32)
+    ks = rng.normal(size=(1, 3, 3, 3, 24)).astype(np.float32) * 0.3
+    kt = rng.normal(size=(5, 1, 1, 1, 24)).astype(np.float32) * 0.5
+    bias = np.zeros(24, np.float32)
+    want = np.maximum(np_ops.stem_convs(x, ks, kt), 0.0)
+    got = _ops().stem_fwd(to_dev(x), to_dev(ks.reshape(27, 24)), to_dev(kt.reshape(5, 24)),
+                          to_dev(bias), torch.bfloat16)          # fp32 clips -> bf16 activations
+    assert got.dtype == torch.bfloat16
+    assert_close(to_np(got), want, torch.bfloat16, "stem f32->bf16")
+
+
+# ------------------------------------------------------------------------------- channelwise
+DW_CASES = [  # N, T, H, W, C, stride  -- covers both SAME-pad cases, odd extents, all strip widths
+    (2, 4, 8, 8, 56, 1), (1, 16, 14, 14, 216, 1), (1, 13, 23, 23, 112, 1), (1, 4, 7, 7, 432, 1),
+    (1, 5, 12, 6, 56, 1), (1, 4, 16, 16, 56, 2), (1, 13, 23, 23, 112, 2), (1, 4, 46, 46, 56, 2),
+    (2, 3, 9, 13, 168, 2), (1, 1, 5, 5, 8, 1), (1, 2, 3, 20, 632, 1), (1, 16, 28, 28, 112, 1)]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("N,T,H,W,C,stride", DW_CASES)
+def test_channelwise(dtype, N, T, H, W, C, stride):
+    from x3d_tf_b200.arch import same_pad
+    rng = np.random.default_rng(H * 100 + W + C + stride)
+    x = _q(rng.normal(size=(N, T, H, W, C)), dtype)
+    k = rng.normal(size=(3, 3, 3, 1, C)).astype(np.float32) * 0.3
+    bias = rng.normal(size=C).astype(np.float32) * 0.2
+    want = np_ops.channelwise_conv_same(x, k, stride) + bias
+    _, ph, _ = same_pad(H, 3, stride)
+    _, pw, _ = same_pad(W, 3, stride)
+    out, partial = _ops().dw_fwd(to_dev(x, dtype), to_dev(k.reshape(27, C)), to_dev(bias), stride,
+                                 ph, pw, True)
+    assert_close(to_np(out), want, dtype, "channelwise")
+    # SE partial sums: fp32 sums of the unrounded outputs
+    sums = to_np(partial).astype(np.float64).sum(1)
+    np.testing.assert_allclose(sums, want.sum((1, 2, 3)), rtol=2e-4,
+                               atol=2e-4 * np.abs(want).sum((1, 2, 3)).max())
+    out2, p2 = _ops().dw_fwd(to_dev(x, dtype), to_dev(k.reshape(27, C)), to_dev(bias), stride,
+                             ph, pw, False)
+    assert p2 is None and torch.equal(out, out2)
+
+
+# ------------------------------------------------------------------------------- pointwise
+def _pw_ref(a, w, bias, res=None, se=None, rpc=0, swish=False, relu=False):
+    a = np.asarray(a, np.float64)
+    if se is not None:
+        a = a * np.repeat(se.astype(np.float64), rpc, axis=0)[: a.shape[0]]
+    if swish:
+        a = a / (1.0 + np.exp(-a))
+    y = a @ w.astype(np.float64) + bias
+    if res is not None:
+        y = y + res
+    return np.maximum(y, 0) if relu else y
+
+
+PW_CASES = [(1000, 24, 56), (300, 56, 24), (4097, 112, 48), (129, 216, 96), (784, 192, 432),
+            (50, 432, 192), (128, 8, 8), (77, 632, 280)]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("M,K,N", PW_CASES)
+def test_pointwise_simt_plain(dtype, M, K, N):
+    rng = np.random.default_rng(M + K + N)
+    a = _q(rng.normal(size=(M, K)), dtype)
+    w = rng.normal(size=(K, N)).astype(np.float32) / np.sqrt(K)
+    bias = rng.normal(size=N).astype(np.float32)
+    got = _ops().pw_fwd(to_dev(a, dtype), to_dev(w), to_dev(bias), M=M, K=K, Nc=N, relu=True)
+    assert_close(to_np(got), _pw_ref(a, w, bias, relu=True), dtype, "pw simt")
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_pointwise_simt_prologue_epilogue(dtype):
+    rng = np.random.default_rng(5)
+    M, K, N, rpc = 600, 112, 48, 200
+    a = _q(rng.normal(size=(M, K)), dtype)
+    w = rng.normal(size=(K, N)).astype(np.float32) / np.sqrt(K)
+    bias = rng.normal(size=N).astype(np.float32)
+    res = _q(rng.normal(size=(M, N)), dtype)
+    se = rng.uniform(0.1, 0.9, size=(3, K)).astype(np.float32)
+    got = _ops().pw_fwd(to_dev(a, dtype), to_dev(w), to_dev(bias), M=M, K=K, Nc=N,
+                        residual=to_dev(res, dtype), se=to_dev(se), rows_per_clip=rpc, swish=True,
+                        relu=True)
+    assert_close(to_np(got), _pw_ref(a, w, bias, res, se, rpc, True, True), dtype, "pw simt pro/epi")
+    got = _ops().pw_fwd(to_dev(a, dtype), to_dev(w), to_dev(bias), M=M, K=K, Nc=N, swish=True)
+    assert_close(to_np(got), _pw_ref(a, w, bias, swish=True), dtype, "pw simt swish only")
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("H,W", [(8, 8), (7, 9), (23, 23)])
+def test_pointwise_strided_gather(dtype, H, W):
+    rng = np.random.default_rng(H + W)
+    N, T, K, Nc = 2, 3, 24, 48
+    x = _q(rng.normal(size=(N, T, H, W, K)), dtype)
+    k = rng.normal(size=(1, 1, 1, K, Nc)).astype(np.float32) / 5
+    bias = rng.normal(size=Nc).astype(np.float32)
+    want = np_ops.pointwise_conv_valid(x, k, 2) + bias
+    Ho, Wo = want.shape[2:4]
+    got = _ops().pw_fwd(to_dev(x, dtype), to_dev(k.reshape(K, Nc)), to_dev(bias),
+                        M=N * T * Ho * Wo, K=K, Nc=Nc, gather=(T, Ho, Wo, H, W, 2))
+    assert_close(to_np(got).reshape(want.shape), want, dtype, "shortcut gather")
+
+
+def _pack_tc(w, scale=None):
+    K, N = w.shape
+    npad, kpad = (N + 15) // 16 * 16, (K + 63) // 64 * 64
+    wp = np.zeros((npad, kpad), np.float32)
+    wp[:N, :K] = w.T
+    return to_dev(wp, torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,K,N", PW_CASES + [(128 * 300 + 5, 56, 24), (20000, 24, 56)])
+def test_pointwise_tcgen05_plain(M, K, N):
+    rng = np.random.default_rng(M + K + N)
+    a = bf16_round(rng.normal(size=(M, K)))
+    w = bf16_round(rng.normal(size=(K, N)) / np.sqrt(K))
+    bias = rng.normal(size=N).astype(np.float32)
+    got = _ops().pw_tc_fwd(to_dev(a, torch.bfloat16), _pack_tc(w), to_dev(bias), M=M, K=K, Nc=N,
+                           relu=True)
+    torch.cuda.synchronize()
+    assert_close(to_np(got), _pw_ref(a, w, bias, relu=True), torch.bfloat16, "pw tcgen05")
+
+
+def test_pointwise_tcgen05_prologue_epilogue():
+    rng = np.random.default_rng(11)
+    for (M, K, N, rpc) in [(600, 112, 48, 200), (5000, 216, 96, 784), (1500, 56, 24, 100),
+                           (900, 432, 192, 300)]:
+        a = bf16_round(rng.normal(size=(M, K)))
+        w = bf16_round(rng.normal(size=(K, N)) / np.sqrt(K))
+        bias = rng.normal(size=N).astype(np.float32)
+        res = bf16_round(rng.normal(size=(M, N)))
+        nclip = -(-M // rpc)
+        se = rng.uniform(0.1, 0.9, size=(nclip, K)).astype(np.float32)
+        got = _ops().pw_tc_fwd(to_dev(a, torch.bfloat16), _pack_tc(w), to_dev(bias), M=M, K=K,
+                               Nc=N, residual=to_dev(res, torch.bfloat16), se=to_dev(se),
+                               rows_per_clip=rpc, swish=True, relu=True)
+        torch.cuda.synchronize()
+        # the prologue rounds swish(se*a) to bf16 before the MMA: allow one more bf16 ulp of scale
+        want = _pw_ref(a, w, bias, res, se, rpc, True, True)
+        assert rel_err(to_np(got), want) < 1.2e-2, (M, K, N)
+        got2 = _ops().pw_tc_fwd(to_dev(a, torch.bfloat16), _pack_tc(w), to_dev(bias), M=M, K=K,
+                                Nc=N, swish=True)
+        assert rel_err(to_np(got2), _pw_ref(a, w, bias, swish=True)) < 1.2e-2
+
+
+def test_pointwise_tcgen05_matches_simt_bitwise_inputs():
+    """Same bf16 inputs through both pointwise kernels: results agree to bf16 rounding."""
+    rng = np.random.default_rng(3)
+    M, K, N = 3000, 96, 216
+    a = bf16_round(rng.normal(size=(M, K)))
+    w = bf16_round(rng.normal(size=(K, N)) / np.sqrt(K))
+    bias = rng.normal(size=N).astype(np.float32)
+    t1 = _ops().pw_tc_fwd(to_dev(a, torch.bfloat16), _pack_tc(w), to_dev(bias), M=M, K=K, Nc=N)
+    t2 = _ops().pw_fwd(to_dev(a, torch.bfloat16), to_dev(w), to_dev(bias), M=M, K=K, Nc=N)
+    assert rel_err(to_np(t1), to_np(t2).astype(np.float64)) < 2.0 ** -7
+
+
+# ------------------------------------------------------------------------------- small kernels
+def test_se_mlp():
+    rng = np.random.default_rng(2)
+    N, nblk, C, Cw = 3, 5, 112, 8
+    partial = rng.normal(size=(N, nblk, C)).astype(np.float32)
+    w1 = rng.normal(size=(C, Cw)).astype(np.float32) / 5
+    b1 = rng.normal(size=Cw).astype(np.float32)
+    w2 = rng.normal(size=(Cw, C)).astype(np.float32)
+    b2 = rng.normal(size=C).astype(np.float32)
+    count = 77
+    mean = partial.astype(np.float64).sum(1) / count
+    z = np.maximum(mean @ w1 + b1, 0)
+    want = 1 / (1 + np.exp(-(z @ w2 + b2)))
+    got = _ops().se_mlp_fwd(to_dev(partial), count, to_dev(w1), to_dev(b1), to_dev(w2), to_dev(b2))
+    np.testing.assert_allclose(to_np(got), want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_avgpool(dtype):
+    rng = np.random.default_rng(4)
+    x = _q(rng.normal(size=(3, 4, 7, 7, 432)), dtype)
+    got = _ops().avgpool_fwd(to_dev(x, dtype))
+    np.testing.assert_allclose(to_np(got), x.astype(np.float64).mean((1, 2, 3)), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("num_preds", [1, 2, 10])
+def test_softmax_viewmean(num_preds):
+    rng = np.random.default_rng(num_preds)
+    lg = (rng.normal(size=(20, 400)) * 4).astype(np.float32)
+    p = np.exp(lg.astype(np.float64) - lg.max(-1, keepdims=True))
+    p /= p.sum(-1, keepdims=True)
+    want = p.reshape(-1, num_preds, 400).mean(1)
+    got = _ops().softmax_viewmean_fwd(to_dev(lg), num_preds)
+    np.testing.assert_allclose(to_np(got), want, rtol=2e-6, atol=1e-9)
+    if num_preds == 2:
+        with pytest.raises(ValueError):
+            _ops().softmax_viewmean_fwd(to_dev(lg[:19]), 2)
+
+
+def test_error_reporting():
+    from x3d_tf_b200._lib import X3DLibError
+    x = torch.zeros((1, 2, 4, 4, 12), device=dev())            # C not a multiple of 8
+    with pytest.raises(X3DLibError, match="multiple of 8"):
+        _ops().dw_fwd(x, torch.zeros((27, 12), device=dev()), torch.zeros(12, device=dev()), 1, 1, 1, False)
+    with pytest.raises(ValueError):
+        _ops().avgpool_fwd(torch.zeros((1, 2, 2, 2, 8)))       # CPU tensor: no CPU path

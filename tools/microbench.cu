@@ -1,0 +1,70 @@
+// Microbenchmarks that size the channelwise/stem kernels: fp32 FMA issue rate with FFMA vs the
+// packed FFMA2, bf16 HFMA2, and a plain 128-bit copy.   nvcc -arch=sm_100a -O3 -o microbench microbench.cu
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+template <int MODE>
+__global__ void fma_kernel(float* out, int iters, float a0) {
+  float2 acc[8];
+  __nv_bfloat162 hacc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i] = make_float2(threadIdx.x * 1e-3f + i, i); hacc[i] = __floats2bfloat162_rn(i, i + 1); }
+  float2 a = make_float2(a0, a0 * 0.5f), b = make_float2(0.25f, 0.125f);
+  __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a0), hb = __floats2bfloat162_rn(0.25f, 0.5f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (MODE == 0) { acc[i].x = fmaf(acc[i].x, a.x, b.x); acc[i].y = fmaf(acc[i].y, a.y, b.y); }
+      if (MODE == 1) { acc[i] = __ffma2_rn(acc[i], a, b); }
+      if (MODE == 2) { hacc[i] = __hfma2(hacc[i], ha, hb); }
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i].x + acc[i].y + __low2float(hacc[i]) + __high2float(hacc[i]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void copy_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    uint4 a = in[i], b = in[i + stride], c = in[i + 2 * stride], d = in[i + 3 * stride];
+    out[i] = a; out[i + stride] = b; out[i + 2 * stride] = c; out[i + 3 * stride] = d;
+  }
+  for (; i < n; i += stride) out[i] = in[i];
+}
+
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  printf("device %s, %d SMs, clock %d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
+  float* out; cudaMalloc(&out, 148 * 8 * 1024 * sizeof(float));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int iters = 20000, blocks = p.multiProcessorCount * 4, threads = 512;
+  const char* names[3] = {"FFMA (2 per lane-iter)", "FFMA2", "HFMA2.BF16"};
+  for (int mode = 0; mode < 3; ++mode) {
+    for (int rep = 0; rep < 2; ++rep) {
+      cudaEventRecord(e0);
+      if (mode == 0) fma_kernel<0><<<blocks, threads>>>(out, iters, 1.0001f);
+      if (mode == 1) fma_kernel<1><<<blocks, threads>>>(out, iters, 1.0001f);
+      if (mode == 2) fma_kernel<2><<<blocks, threads>>>(out, iters, 1.0001f);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      double fmas = (double)blocks * threads * iters * 8 * 2;
+      if (rep) printf("%-24s %8.3f ms  %8.2f TFMA/s  (%.1f FMA/clk/SM at %d MHz nominal)\n", names[mode], ms,
+                      fmas / ms / 1e9, fmas / (ms * 1e-3) / p.multiProcessorCount / (p.clockRate * 1e3), p.clockRate / 1000);
+    }
+  }
+  size_t n = (size_t)1 << 26;   // 1 GiB in uint4
+  uint4 *a, *b; cudaMalloc(&a, n * 16); cudaMalloc(&b, n * 16); cudaMemset(a, 1, n * 16);
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    copy_kernel<<<p.multiProcessorCount * 8, 512>>>(a, b, n);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep) printf("copy 1 GiB: %.3f ms  %.1f GB/s (read+write)\n", ms, 2.0 * n * 16 / ms / 1e6);
+  }
+  printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}

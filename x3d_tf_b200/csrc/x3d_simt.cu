@@ -1,0 +1,595 @@
+// CUDA-core (SIMT) kernels of the X3D forward path for sm_100a:
+//   stem (fused conv_s + conv_t + BN + ReLU), channelwise 3x3x3 stencil (+BN, +SE partial sums),
+//   SE MLP, global average pool, softmax + view mean, and the generic fp32-accumulate pointwise
+//   GEMM used by the fp32 path, the strided shortcut conv and the head.
+// The bf16 tensor-core pointwise GEMM lives in x3d_pw_tc.cu.
+#include "common.cuh"
+
+namespace x3d {
+
+// =====================================================================================
+// Stem.  One CTA = one 8x16 output tile of one clip (and one chunk of <=32 channels), marching
+// over the T frames: per frame the 17x33x3 input patch is staged in shared memory, every thread
+// evaluates conv_s for its channel pair on up to 8 pixels (weights live in registers), pushes the
+// result into a 5-deep register ring and emits conv_t + BN + ReLU for frame t-2.  Input is read
+// once, output written once; conv_s results never leave registers.
+constexpr int kStemTH = 8, kStemTW = 16, kStemPix = kStemTH * kStemTW;
+constexpr int kStemIH = 2 * kStemTH + 1, kStemIW3 = (2 * kStemTW + 1) * 3, kStemPitch = 100;
+constexpr int kStemThreads = 256, kStemNP = 8, kStemKT = 5;
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kStemThreads)
+stem_kernel(const TI* __restrict__ in, const float* __restrict__ ws, const float* __restrict__ wt,
+            const float* __restrict__ bias, TO* __restrict__ out, int T, int H, int W, int Ho,
+            int Wo, int C, int cchunks) {
+  __shared__ float s_in[kStemIH * kStemPitch];
+  const int tid = threadIdx.x;
+  const int n = blockIdx.z / cchunks, cc = blockIdx.z % cchunks;
+  const int c_lo = cc * 32;
+  const int c2c = (min(C, c_lo + 32) - c_lo) >> 1;          // channel pairs in this chunk
+  const int PL = kStemThreads / c2c;                         // pixel lanes
+  const int cp = tid % c2c, pl = tid / c2c;
+  const bool lane_on = pl < PL;
+  const int c = c_lo + 2 * cp;
+  const int ho0 = blockIdx.y * kStemTH, wo0 = blockIdx.x * kStemTW;
+
+  float2 wsr[27], wtr[kStemKT];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) wsr[i] = ld2(ws + i * C + c);
+#pragma unroll
+  for (int i = 0; i < kStemKT; ++i) wtr[i] = ld2(wt + i * C + c);
+  const float2 b = ld2(bias + c);
+
+  int soff[kStemNP];          // smem offset of each pixel's patch; -1 = pixel not in tile
+  long ooff[kStemNP];         // output offset inside one frame; -1 = outside the image
+#pragma unroll
+  for (int i = 0; i < kStemNP; ++i) {
+    const int pix = pl + i * PL;
+    const int py = pix / kStemTW, px = pix % kStemTW;
+    const bool in_tile = lane_on && pix < kStemPix;
+    soff[i] = in_tile ? (2 * py) * kStemPitch + 2 * px * 3 : -1;
+    const int ho = ho0 + py, wo = wo0 + px;
+    ooff[i] = (in_tile && ho < Ho && wo < Wo) ? ((long)ho * Wo + wo) * C + c : -1;
+  }
+
+  float2 ring[kStemKT][kStemNP];
+#pragma unroll
+  for (int d = 0; d < kStemKT; ++d)
+#pragma unroll
+    for (int i = 0; i < kStemNP; ++i) ring[d][i] = make_float2(0.f, 0.f);
+
+  const long in_frame = (long)H * W * 3;
+  const TI* in_n = in + (long)n * T * in_frame;
+  TO* out_n = out + (long)n * T * Ho * Wo * C;
+  const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1;
+
+  for (int t = 0; t < T + kStemKT / 2; ++t) {
+    if (t < T) {
+      const TI* fr = in_n + (long)t * in_frame;
+      for (int idx = tid; idx < kStemIH * kStemIW3; idx += kStemThreads) {
+        const int r = idx / kStemIW3, e = idx - r * kStemIW3;
+        const int hi = hi0 + r, wi = wi0 + e / 3;
+        float v = 0.f;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = ld1(fr + ((long)hi * W + wi0) * 3 + e);
+        s_in[r * kStemPitch + e] = v;
+      }
+    }
+    __syncthreads();
+    // shift the ring, then push conv_s(frame t) (zero beyond the clip: temporal zero padding)
+#pragma unroll
+    for (int d = 0; d + 1 < kStemKT; ++d)
+#pragma unroll
+      for (int i = 0; i < kStemNP; ++i) ring[d][i] = ring[d + 1][i];
+#pragma unroll
+    for (int i = 0; i < kStemNP; ++i) {
+      float2 acc = make_float2(0.f, 0.f);
+      if (t < T && soff[i] >= 0) {
+        const float* p = s_in + soff[i];
+#pragma unroll
+        for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+          for (int q = 0; q < 9; ++q) {
+            const float x = p[dh * kStemPitch + q];
+            acc = fma2(make_float2(x, x), wsr[dh * 9 + q], acc);
+          }
+      }
+      ring[kStemKT - 1][i] = acc;
+    }
+    const int to = t - kStemKT / 2;
+    if (to >= 0) {
+      TO* of = out_n + (long)to * Ho * Wo * C;
+#pragma unroll
+      for (int i = 0; i < kStemNP; ++i) {
+        if (ooff[i] < 0) continue;
+        float2 y = b;
+#pragma unroll
+        for (int d = 0; d < kStemKT; ++d) y = fma2(ring[d][i], wtr[d], y);
+        y.x = fmaxf(y.x, 0.f);
+        y.y = fmaxf(y.y, 0.f);
+        st2(of + ooff[i], y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// =====================================================================================
+// Channelwise 3x3x3 stencil + BN (+ SE partial sums).
+// A thread owns one channel pair (its 27 taps x 2 channels stay in registers for the whole
+// kernel) and computes register blocks of 2 frames x SW output columns: 4 input frames x 3 rows
+// x ((SW-1)*S+3) columns are loaded once each and reused across the 2x3 temporal/column taps.
+// blockDim.x = (C/2) * k_slots: `slot` selects which block of a group of k_slots the thread works
+// on, so warps read contiguous channel runs (coalesced) with no idle lanes.
+template <typename T, int S, int SW>
+__global__ void __launch_bounds__(384)
+dw3x3x3_kernel(const T* __restrict__ in, const float* __restrict__ w,
+               const float* __restrict__ bias, T* __restrict__ out, float* __restrict__ partial,
+               int Tn, int H, int W, int Ho, int Wo, int Cs, int pad_h, int pad_w, int strips_w,
+               int total_strips, int k_slots) {
+  constexpr int NCOL = (SW - 1) * S + 3;
+  extern __shared__ float s_red[];                 // [k_slots][Cs] when partial != nullptr
+  const int C2 = Cs >> 1;
+  const int tid = threadIdx.x;
+  const int slot = tid / C2, cp = tid - slot * C2;
+  const bool on = slot < k_slots;
+  const int n = blockIdx.y;
+  const int c = cp * 2;
+
+  float2 wr[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) wr[i] = ld2(w + i * Cs + c);
+  const float2 b = ld2(bias + c);
+  float2 ssum = make_float2(0.f, 0.f);
+
+  const T* in_n = in + (long)n * Tn * H * W * Cs;
+  T* out_n = out + (long)n * Tn * Ho * Wo * Cs;
+
+  if (on) {
+    for (int s = blockIdx.x * k_slots + slot; s < total_strips; s += gridDim.x * k_slots) {
+      const int wsi = s % strips_w;
+      const int r = s / strips_w;
+      const int ho = r % Ho, tp = r / Ho;
+      const int t0 = tp * 2, wo0 = wsi * SW;
+      const int wi0 = wo0 * S - pad_w;
+      float2 acc[2][SW];
+#pragma unroll
+      for (int f = 0; f < 2; ++f)
+#pragma unroll
+        for (int j = 0; j < SW; ++j) acc[f][j] = make_float2(0.f, 0.f);
+
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ti = t0 - 1 + i;
+        if (ti < 0 || ti >= Tn) continue;
+#pragma unroll
+        for (int dh = 0; dh < 3; ++dh) {
+          const int hi = ho * S - pad_h + dh;
+          if (hi < 0 || hi >= H) continue;
+          const T* row = in_n + ((long)(ti * H + hi) * W) * Cs + c;
+          float2 v[NCOL];
+#pragma unroll
+          for (int j = 0; j < NCOL; ++j) {
+            const int wi = wi0 + j;
+            v[j] = (wi >= 0 && wi < W) ? ld2(row + (long)wi * Cs) : make_float2(0.f, 0.f);
+          }
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            const int dt = i - f;            // input frame ti is tap dt of output frame t0+f
+            if (dt < 0 || dt > 2) continue;  // resolved at compile time (i, f unrolled)
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw) {
+              const float2 wg = wr[(dt * 3 + dh) * 3 + dw];
+#pragma unroll
+              for (int j = 0; j < SW; ++j) acc[f][j] = fma2(v[j * S + dw], wg, acc[f][j]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        const int t = t0 + f;
+        if (t >= Tn) continue;
+        T* orow = out_n + ((long)(t * Ho + ho) * Wo) * Cs + c;
+#pragma unroll
+        for (int j = 0; j < SW; ++j) {
+          const int wo = wo0 + j;
+          if (wo >= Wo) continue;
+          float2 y = make_float2(acc[f][j].x + b.x, acc[f][j].y + b.y);
+          st2(orow + (long)wo * Cs, y);
+          ssum.x += y.x;
+          ssum.y += y.y;
+        }
+      }
+    }
+  }
+  if (partial != nullptr) {
+    if (on) {
+      s_red[slot * Cs + c] = ssum.x;
+      s_red[slot * Cs + c + 1] = ssum.y;
+    }
+    __syncthreads();
+    if (tid < Cs) {
+      float a = 0.f;
+      for (int k = 0; k < k_slots; ++k) a += s_red[k * Cs + tid];
+      partial[((long)n * gridDim.x + blockIdx.x) * Cs + tid] = a;
+    }
+  }
+}
+
+// =====================================================================================
+// SE MLP: one CTA per clip.
+__global__ void __launch_bounds__(256)
+se_mlp_kernel(const float* __restrict__ partial, int nblk, float inv_count,
+              const float* __restrict__ w1, const float* __restrict__ b1,
+              const float* __restrict__ w2, const float* __restrict__ b2,
+              float* __restrict__ scale, int C, int Cw) {
+  extern __shared__ float sm[];      // mean[C] | z[Cw]
+  float* mean = sm;
+  float* z = sm + C;
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const float* p = partial + (long)n * nblk * C;
+  for (int c = tid; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < nblk; ++k) a += p[(long)k * C + c];
+    mean[c] = a * inv_count;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+  for (int j = warp; j < Cw; j += nwarp) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(mean[c], w1[(long)c * Cw + j], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) z[j] = fmaxf(a + b1[j], 0.f);
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) {
+    float a = b2[c];
+    for (int j = 0; j < Cw; ++j) a = fmaf(z[j], w2[(long)j * C + c], a);
+    scale[(long)n * C + c] = 1.f / (1.f + expf(-a));
+  }
+}
+
+// =====================================================================================
+// Global average pool [N,P,C] -> [N,C] fp32.  grid (C/64 chunks, N); 256 threads = 4 row groups
+// x 64 channels; fixed-order reduction.
+template <typename T>
+__global__ void __launch_bounds__(256)
+avgpool_kernel(const T* __restrict__ in, float* __restrict__ out, long P, int C) {
+  __shared__ float red[4][64];
+  const int n = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63), g = threadIdx.x >> 6;
+  float a = 0.f;
+  if (c < C) {
+    const T* p = in + (long)n * P * C + c;
+    for (long r = g; r < P; r += 4) a += ld1(p + r * C);
+  }
+  red[g][threadIdx.x & 63] = a;
+  __syncthreads();
+  if (g == 0 && c < C) {
+    const int l = threadIdx.x;
+    out[(long)n * C + c] = (red[0][l] + red[1][l] + red[2][l] + red[3][l]) / (float)P;
+  }
+}
+
+// =====================================================================================
+// Softmax over classes (fp32) and mean over the num_preds consecutive clips of a video.
+__device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, u) : v + u;
+  }
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int i = 1; i < nw; ++i) r = is_max ? fmaxf(r, sh[i]) : r + sh[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+softmax_viewmean_kernel(const float* __restrict__ logits, float* __restrict__ probs, int ncls,
+                        int num_preds) {
+  __shared__ float sh[8];
+  const int vid = blockIdx.x;
+  const float inv = 1.f / (float)num_preds;
+  for (int c = threadIdx.x; c < ncls; c += blockDim.x) probs[(long)vid * ncls + c] = 0.f;
+  for (int v = 0; v < num_preds; ++v) {
+    const float* row = logits + ((long)vid * num_preds + v) * ncls;
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < ncls; c += blockDim.x) m = fmaxf(m, row[c]);
+    m = block_reduce(m, sh, true);
+    float s = 0.f;
+    for (int c = threadIdx.x; c < ncls; c += blockDim.x) s += expf(row[c] - m);
+    s = block_reduce(s, sh, false);
+    const float k = inv / s;
+    for (int c = threadIdx.x; c < ncls; c += blockDim.x)
+      probs[(long)vid * ncls + c] += expf(row[c] - m) * k;
+  }
+}
+
+// =====================================================================================
+// Generic pointwise GEMM, fp32 accumulate on CUDA cores.  128x64 output tile, BK = 16,
+// 256 threads, 8x4 outputs per thread.
+constexpr int kBM = 128, kBN = 64, kBK = 16, kAPitch = kBM + 4;
+
+struct PwParams {
+  const void* A; const float* Wt; const float* bias; const void* R; const float* se; void* D;
+  long M; int K, Nc, lda, ldw, ldr, ldd;
+  long rows_per_clip;
+  int swish, relu, gather, T, Ho, Wo, Hi, Wi, stride;
+};
+
+template <typename TA, typename TD, bool kFast>
+__global__ void __launch_bounds__(256)
+pw_gemm_kernel(const PwParams p) {
+  __shared__ __align__(16) float As[kBK][kAPitch];
+  __shared__ __align__(16) float Ws[kBK][kBN];
+  const int tid = threadIdx.x;
+  const long m0 = (long)blockIdx.x * kBM;
+  const int n0 = blockIdx.y * kBN;
+  const TA* A = static_cast<const TA*>(p.A);
+
+  // loader role: row lr, k-half lk (8 consecutive k)
+  const int lr = tid >> 1, lk = (tid & 1) * 8;
+  const long lm = m0 + lr;
+  long arow = -1;
+  long clip = 0;
+  if (lm < p.M) {
+    arow = lm;
+    if (p.gather) {
+      long q = lm;
+      const int wo = (int)(q % p.Wo); q /= p.Wo;
+      const int ho = (int)(q % p.Ho); q /= p.Ho;       // q = n*T + t
+      arow = (q * p.Hi + (long)ho * p.stride) * p.Wi + (long)wo * p.stride;
+    }
+    if (p.se) clip = lm / p.rows_per_clip;
+  }
+  // W loader role
+  const int wk = tid >> 4, wn = (tid & 15) * 4;
+
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < p.K; k0 += kBK) {
+    float av[8];
+    const int ka = k0 + lk;
+    if (arow >= 0 && ka < p.K) {
+      ld8(A + arow * p.lda + ka, av);
+      if (p.se) {
+        const float* sp = p.se + clip * p.K + ka;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) av[i] *= __ldg(sp + i);
+      }
+      if (p.swish) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) av[i] = av[i] * sigmoidf_<kFast>(av[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) av[i] = 0.f;
+    }
+    float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k0 + wk < p.K && n0 + wn < p.Nc)
+      wv = __ldg(reinterpret_cast<const float4*>(p.Wt + (long)(k0 + wk) * p.ldw + n0 + wn));
+    __syncthreads();          // previous tile fully consumed
+#pragma unroll
+    for (int i = 0; i < 8; ++i) As[lk + i][lr] = av[i];
+    *reinterpret_cast<float4*>(&Ws[wk][wn]) = wv;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+  }
+
+  const int col = n0 + tx * 4;
+  if (col >= p.Nc) return;
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.bias) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+  }
+  TD* D = static_cast<TD*>(p.D);
+  const TD* R = static_cast<const TD*>(p.R);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long m = m0 + ty * 8 + i;
+    if (m >= p.M) continue;
+    float y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = acc[i][j] + bv[j];
+    if (R) {
+      float rv[4];
+      ld4(R + m * p.ldr + col, rv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] += rv[j];
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
+    }
+    st4(D + m * p.ldd + col, y);
+  }
+}
+
+// --------------------------------------------------------------------------- host side
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+template <typename T, int STRIDE, int SW>
+static int launch_dw(const void* in, const float* w, const float* bias, void* out,
+                     float* partial, int N, int Tn, int H, int W, int Ho, int Wo, int C,
+                     int pad_h, int pad_w, int nblk, cudaStream_t st) {
+  const int C2 = C / 2;
+  const int k_slots = max(1, 256 / C2);
+  const int threads = ((C2 * k_slots + 31) / 32) * 32;
+  const int strips_w = (Wo + SW - 1) / SW;
+  const int total = ((Tn + 1) / 2) * Ho * strips_w;
+  const size_t smem = partial ? sizeof(float) * k_slots * C : 0;
+  dim3 grid(nblk, N);
+  dw3x3x3_kernel<T, STRIDE, SW><<<grid, threads, smem, st>>>(
+      static_cast<const T*>(in), w, bias, static_cast<T*>(out), partial, Tn, H, W, Ho, Wo, C,
+      pad_h, pad_w, strips_w, total, k_slots);
+  return check_launch("x3d_dw3x3x3_fwd");
+}
+
+static int dw_strip_width(int Wo, int stride) {
+  // candidate widths compiled in: stride 1 -> {4,7,8}; stride 2 -> {4}
+  if (stride == 2) return 4;
+  int best = 8, best_cost = ((Wo + 7) / 8) * 8;
+  const int cand[2] = {7, 4};
+  for (int k = 0; k < 2; ++k) {
+    const int cost = ((Wo + cand[k] - 1) / cand[k]) * cand[k];
+    if (cost < best_cost) { best = cand[k]; best_cost = cost; }
+  }
+  return best;
+}
+
+static int dw_blocks(int Tn, int H, int W, int C, int stride) {
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  const int SW = dw_strip_width(Wo, stride);
+  const int strips_w = (Wo + SW - 1) / SW;
+  const int total = ((Tn + 1) / 2) * Ho * strips_w;
+  const int k_slots = max(1, 256 / (C / 2));
+  // aim at ~4 register blocks per thread, at most 256 partial rows per clip
+  int nblk = (total + k_slots * 4 - 1) / (k_slots * 4);
+  return max(1, min(nblk, 256));
+}
+
+}  // namespace x3d
+
+using namespace x3d;
+
+extern "C" {
+
+int x3d_stem_fwd(const void* in, int in_dtype, const float* ws, const float* wt,
+                 const float* bias, void* out, int out_dtype, int N, int T, int H, int W, int C,
+                 int kt, void* stream) {
+  X3D_REQUIRE(in && ws && wt && bias && out, X3D_ERR_INVALID_ARG, "x3d_stem_fwd: null pointer");
+  X3D_REQUIRE(kt == kStemKT, X3D_ERR_UNSUPPORTED, "x3d_stem_fwd: temporal filter %d (only 5)", kt);
+  X3D_REQUIRE(C > 0 && C % 8 == 0, X3D_ERR_INVALID_ARG, "x3d_stem_fwd: C=%d not a multiple of 8", C);
+  X3D_REQUIRE(N > 0 && T > 0 && H > 0 && W > 0, X3D_ERR_INVALID_ARG, "x3d_stem_fwd: empty input");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int cchunks = (C + 31) / 32;
+  X3D_REQUIRE((long)N * cchunks <= 65535, X3D_ERR_UNSUPPORTED, "x3d_stem_fwd: batch too large for one launch");
+  dim3 grid((Wo + kStemTW - 1) / kStemTW, (Ho + kStemTH - 1) / kStemTH, N * cchunks);
+  cudaStream_t st = S(stream);
+#define X3D_STEM(TI, TO)                                                                         \
+  stem_kernel<TI, TO><<<grid, kStemThreads, 0, st>>>(static_cast<const TI*>(in), ws, wt, bias,   \
+                                                     static_cast<TO*>(out), T, H, W, Ho, Wo, C,  \
+                                                     cchunks)
+  if (in_dtype == X3D_F32 && out_dtype == X3D_F32) X3D_STEM(float, float);
+  else if (in_dtype == X3D_F32 && out_dtype == X3D_BF16) X3D_STEM(float, bf16);
+  else if (in_dtype == X3D_BF16 && out_dtype == X3D_BF16) X3D_STEM(bf16, bf16);
+  else if (in_dtype == X3D_BF16 && out_dtype == X3D_F32) X3D_STEM(bf16, float);
+  else X3D_REQUIRE(false, X3D_ERR_INVALID_ARG, "x3d_stem_fwd: bad dtype %d/%d", in_dtype, out_dtype);
+#undef X3D_STEM
+  return check_launch("x3d_stem_fwd");
+}
+
+int x3d_dw_partial_blocks(int T, int H, int W, int C, int stride) {
+  if (T <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 || (stride != 1 && stride != 2)) return 0;
+  return dw_blocks(T, H, W, C, stride);
+}
+
+int x3d_dw3x3x3_fwd(const void* in, const float* w, const float* bias, void* out,
+                    float* se_partial, int N, int T, int H, int W, int C, int stride, int pad_h,
+                    int pad_w, int dtype, void* stream) {
+  X3D_REQUIRE(in && w && bias && out, X3D_ERR_INVALID_ARG, "x3d_dw3x3x3_fwd: null pointer");
+  X3D_REQUIRE(C > 0 && C % 8 == 0, X3D_ERR_INVALID_ARG, "x3d_dw3x3x3_fwd: C=%d not a multiple of 8", C);
+  X3D_REQUIRE(C / 2 <= 384, X3D_ERR_UNSUPPORTED, "x3d_dw3x3x3_fwd: C=%d > 768", C);
+  X3D_REQUIRE(stride == 1 || stride == 2, X3D_ERR_UNSUPPORTED, "x3d_dw3x3x3_fwd: stride %d", stride);
+  X3D_REQUIRE(N > 0 && N <= 65535 && T > 0 && H > 0 && W > 0, X3D_ERR_INVALID_ARG, "x3d_dw3x3x3_fwd: bad extent");
+  X3D_REQUIRE(pad_h >= 0 && pad_h <= 1 && pad_w >= 0 && pad_w <= 1, X3D_ERR_INVALID_ARG, "x3d_dw3x3x3_fwd: pad_before must be 0 or 1");
+  X3D_REQUIRE(dtype == X3D_F32 || dtype == X3D_BF16, X3D_ERR_INVALID_ARG, "x3d_dw3x3x3_fwd: dtype %d", dtype);
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  const int nblk = dw_blocks(T, H, W, C, stride);
+  const int SW = dw_strip_width(Wo, stride);
+  cudaStream_t st = S(stream);
+#define X3D_DW(TT, ST, SWW) \
+  return launch_dw<TT, ST, SWW>(in, w, bias, out, se_partial, N, T, H, W, Ho, Wo, C, pad_h, pad_w, nblk, st)
+  if (dtype == X3D_BF16) {
+    if (stride == 2) X3D_DW(bf16, 2, 4);
+    if (SW == 8) X3D_DW(bf16, 1, 8);
+    if (SW == 7) X3D_DW(bf16, 1, 7);
+    X3D_DW(bf16, 1, 4);
+  } else {
+    if (stride == 2) X3D_DW(float, 2, 4);
+    if (SW == 8) X3D_DW(float, 1, 8);
+    if (SW == 7) X3D_DW(float, 1, 7);
+    X3D_DW(float, 1, 4);
+  }
+#undef X3D_DW
+}
+
+int x3d_se_mlp_fwd(const float* partial, int nblk, float inv_count, const float* w1,
+                   const float* b1, const float* w2, const float* b2, float* scale, int N, int C,
+                   int Cw, void* stream) {
+  X3D_REQUIRE(partial && w1 && b1 && w2 && b2 && scale, X3D_ERR_INVALID_ARG, "x3d_se_mlp_fwd: null pointer");
+  X3D_REQUIRE(N > 0 && C > 0 && Cw > 0 && Cw <= 64 && nblk > 0, X3D_ERR_INVALID_ARG, "x3d_se_mlp_fwd: bad size");
+  se_mlp_kernel<<<N, 256, sizeof(float) * (C + Cw), S(stream)>>>(partial, nblk, inv_count, w1, b1,
+                                                               w2, b2, scale, C, Cw);
+  return check_launch("x3d_se_mlp_fwd");
+}
+
+int x3d_avgpool_fwd(const void* in, float* out, int N, int64_t P, int C, int dtype, void* stream) {
+  X3D_REQUIRE(in && out && N > 0 && N <= 65535 && P > 0 && C > 0, X3D_ERR_INVALID_ARG, "x3d_avgpool_fwd: bad argument");
+  dim3 grid((C + 63) / 64, N);
+  if (dtype == X3D_BF16)
+    avgpool_kernel<bf16><<<grid, 256, 0, S(stream)>>>(static_cast<const bf16*>(in), out, P, C);
+  else if (dtype == X3D_F32)
+    avgpool_kernel<float><<<grid, 256, 0, S(stream)>>>(static_cast<const float*>(in), out, P, C);
+  else
+    X3D_REQUIRE(false, X3D_ERR_INVALID_ARG, "x3d_avgpool_fwd: dtype %d", dtype);
+  return check_launch("x3d_avgpool_fwd");
+}
+
+int x3d_softmax_viewmean_fwd(const float* logits, float* probs, int N, int ncls, int num_preds,
+                             void* stream) {
+  X3D_REQUIRE(logits && probs && N > 0 && ncls > 0 && num_preds > 0, X3D_ERR_INVALID_ARG, "x3d_softmax_viewmean_fwd: bad argument");
+  X3D_REQUIRE(N % num_preds == 0, X3D_ERR_INVALID_ARG, "x3d_softmax_viewmean_fwd: batch %d is not a multiple of num_preds %d", N, num_preds);
+  softmax_viewmean_kernel<<<N / num_preds, 256, 0, S(stream)>>>(logits, probs, ncls, num_preds);
+  return check_launch("x3d_softmax_viewmean_fwd");
+}
+
+int x3d_pw_fwd(const x3d_pw_args* a, void* stream) {
+  X3D_REQUIRE(a && a->A && a->Wt && a->D, X3D_ERR_INVALID_ARG, "x3d_pw_fwd: null pointer");
+  X3D_REQUIRE(a->M > 0 && a->K > 0 && a->Nc > 0, X3D_ERR_INVALID_ARG, "x3d_pw_fwd: empty problem");
+  X3D_REQUIRE(a->K % 8 == 0 && a->lda % 8 == 0, X3D_ERR_INVALID_ARG, "x3d_pw_fwd: K=%d/lda=%d must be multiples of 8", a->K, a->lda);
+  X3D_REQUIRE(a->Nc % 4 == 0 && a->ldw % 4 == 0 && a->ldd % 4 == 0 && (!a->R || a->ldr % 4 == 0), X3D_ERR_INVALID_ARG, "x3d_pw_fwd: Nc/ldw/ldd/ldr must be multiples of 4");
+  X3D_REQUIRE(!a->se || a->rows_per_clip > 0, X3D_ERR_INVALID_ARG, "x3d_pw_fwd: rows_per_clip missing");
+  X3D_REQUIRE(!a->gather || (a->stride >= 1 && a->Ho > 0 && a->Wo > 0 && a->Hi > 0 && a->Wi > 0), X3D_ERR_INVALID_ARG, "x3d_pw_fwd: bad gather geometry");
+  PwParams p;
+  p.A = a->A; p.Wt = a->Wt; p.bias = a->bias; p.R = a->R; p.se = a->se; p.D = a->D;
+  p.M = a->M; p.K = a->K; p.Nc = a->Nc; p.lda = a->lda; p.ldw = a->ldw; p.ldr = a->ldr; p.ldd = a->ldd;
+  p.rows_per_clip = a->rows_per_clip; p.swish = a->swish; p.relu = a->relu; p.gather = a->gather;
+  p.T = a->T; p.Ho = a->Ho; p.Wo = a->Wo; p.Hi = a->Hi; p.Wi = a->Wi; p.stride = a->stride;
+  const long mt = (a->M + kBM - 1) / kBM;
+  X3D_REQUIRE(mt <= 2147483647L, X3D_ERR_UNSUPPORTED, "x3d_pw_fwd: M too large");
+  dim3 grid((unsigned)mt, (a->Nc + kBN - 1) / kBN);
+  cudaStream_t st = S(stream);
+  if (a->a_dtype == X3D_F32 && a->d_dtype == X3D_F32)
+    pw_gemm_kernel<float, float, false><<<grid, 256, 0, st>>>(p);
+  else if (a->a_dtype == X3D_BF16 && a->d_dtype == X3D_BF16)
+    pw_gemm_kernel<bf16, bf16, true><<<grid, 256, 0, st>>>(p);
+  else if (a->a_dtype == X3D_BF16 && a->d_dtype == X3D_F32)
+    pw_gemm_kernel<bf16, float, true><<<grid, 256, 0, st>>>(p);
+  else
+    X3D_REQUIRE(false, X3D_ERR_INVALID_ARG, "x3d_pw_fwd: unsupported dtype pair %d/%d", a->a_dtype, a->d_dtype);
+  return check_launch("x3d_pw_fwd");
+}
+
+}  // extern "C"

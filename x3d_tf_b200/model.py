@@ -1,0 +1,657 @@
+"""X3D model and blocks with the reference's Keras class API, executed by sm_100a CUDA kernels.
+
+Drop-in surface (reference `model.py`): `X3D(cfg)`, `X3D_Stem`, `Bottleneck`, `ResBlock`,
+`ResStage`, `AdaptiveAvgPool3D` -- same constructor arguments, `call(input, training=False)`,
+`model.stages[i]._inner_channels`, `load_weights(prefix).expect_partial()`, `summary()`, and the
+TF-checkpoint variable names (`conv1/conv_s/kernel`, `stages/0/stage/layer_with_weights-0/
+bottleneck/a/kernel`, ...).  Inputs are channels-last NDHWC clips.
+
+Everything numeric runs in the C-ABI library (`include/x3d_b200.h`); this file only holds the
+weights (numpy, TF layouts), folds the inference BatchNorm into them, and sequences launches.
+There is no CPU / PyTorch fallback: without the CUDA library or a GPU, `call` raises.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import arch as A
+from . import ops
+from . import tf_bundle
+
+_BN_LEAVES = ("gamma", "beta", "moving_mean", "moving_variance")
+
+
+def _pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def _glorot(rng, shape, fan_in, fan_out):
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+class _LoadStatus:
+    """What `tf.keras.Model.load_weights` returns for TF-format checkpoints (eval.py:81)."""
+
+    def __init__(self, missing, unused):
+        self.missing, self.unused = list(missing), list(unused)
+
+    def expect_partial(self):
+        return self
+
+    def assert_consumed(self):
+        if self.missing or self.unused:
+            raise AssertionError(f"unresolved: missing={self.missing[:3]} unused={self.unused[:3]}")
+        return self
+
+    def assert_existing_objects_matched(self):
+        if self.missing:
+            raise AssertionError(f"variables without a checkpoint value: {self.missing[:3]}")
+        return self
+
+
+class Layer:
+    """Minimal stand-in for `tf.keras.layers.Layer`: named variables (numpy, TF layout), child
+    layers, `__call__(x, training=False)`.  Variables are created at construction with the
+    Keras default initialisers (Glorot-uniform kernels, zeros biases, BN gamma=1/beta=0/mean=0/
+    var=1), so a freshly built layer is usable like in the reference."""
+
+    _init_seed = 0
+
+    def __init__(self, name: Optional[str] = None):
+        self.name = name or type(self).__name__.lower()
+        self._vars: "OrderedDict[str, np.ndarray]" = OrderedDict()
+        self._children: "OrderedDict[str, Layer]" = OrderedDict()
+        self._dev: Dict[tuple, dict] = {}
+
+    # ---- variables
+    def _rng(self):
+        Layer._init_seed += 1
+        return np.random.default_rng(Layer._init_seed)
+
+    def _add_conv(self, key: str, shape: Tuple[int, ...], groups: int = 1):
+        rf = int(np.prod(shape[:-2]))
+        fan_in, fan_out = rf * shape[-2], rf * shape[-1] // groups
+        self._vars[key] = _glorot(self._rng(), shape, fan_in, fan_out)
+
+    def _add_bn(self, key: str, c: int):
+        self._vars[f"{key}/gamma"] = np.ones(c, np.float32)
+        self._vars[f"{key}/beta"] = np.zeros(c, np.float32)
+        self._vars[f"{key}/moving_mean"] = np.zeros(c, np.float32)
+        self._vars[f"{key}/moving_variance"] = np.ones(c, np.float32)
+
+    def _child(self, key: str, layer: "Layer") -> "Layer":
+        self._children[key] = layer
+        return layer
+
+    def named_variables(self, prefix: str = "") -> "OrderedDict[str, np.ndarray]":
+        out: "OrderedDict[str, np.ndarray]" = OrderedDict()
+        for k, v in self._vars.items():
+            out[prefix + k] = v
+        for ck, ch in self._children.items():
+            out.update(ch.named_variables(f"{prefix}{ck}/"))
+        return out
+
+    def set_weights_dict(self, weights: Dict[str, np.ndarray], prefix: str = "",
+                         strict: bool = True) -> List[str]:
+        """Assign variables by (prefixed) checkpoint name.  Returns names that had no value."""
+        missing = []
+        for k in list(self._vars):
+            full = prefix + k
+            if full in weights:
+                w = np.asarray(weights[full], dtype=np.float32)
+                if w.shape != self._vars[k].shape:
+                    raise ValueError(f"{full}: shape {w.shape} != expected {self._vars[k].shape}")
+                self._vars[k] = np.ascontiguousarray(w)
+            else:
+                missing.append(full)
+        for ck, ch in self._children.items():
+            missing += ch.set_weights_dict(weights, f"{prefix}{ck}/", strict=False)
+        self._invalidate()
+        if strict and missing:
+            raise KeyError(f"no value for {len(missing)} variables, e.g. {missing[:3]}")
+        return missing
+
+    def count_params(self) -> int:
+        return sum(int(v.size) for v in self.named_variables().values())
+
+    def _invalidate(self):
+        self._dev.clear()
+        for ch in self._children.values():
+            ch._invalidate()
+
+    # ---- execution
+    def __call__(self, x, training: bool = False):
+        return self.call(x, training=training)
+
+    def call(self, x, training: bool = False):
+        raise NotImplementedError
+
+    @staticmethod
+    def _no_training(training: bool):
+        if training:
+            raise NotImplementedError(
+                "training=True (batch-statistics BatchNorm, dropout) is not built yet; only the "
+                "inference path of model.py:113-127 is implemented (see DESIGN.md, scope)")
+
+    def _fold_bn(self, key: str, eps: float) -> Tuple[np.ndarray, np.ndarray]:
+        g = self._vars[f"{key}/gamma"].astype(np.float64)
+        b = self._vars[f"{key}/beta"].astype(np.float64)
+        m = self._vars[f"{key}/moving_mean"].astype(np.float64)
+        v = self._vars[f"{key}/moving_variance"].astype(np.float64)
+        s = g / np.sqrt(v + eps)
+        return s, b - m * s
+
+
+def _dev_f32(a: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+
+
+def _pad_to(a: np.ndarray, axis: int, size: int) -> np.ndarray:
+    if a.shape[axis] == size:
+        return a
+    pad = [(0, 0)] * a.ndim
+    pad[axis] = (0, size - a.shape[axis])
+    return np.pad(a, pad)
+
+
+def _as_device_clip(x, device) -> torch.Tensor:
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not isinstance(x, torch.Tensor):
+        raise TypeError("input must be a torch.Tensor or numpy array in NDHWC layout")
+    if x.dim() != 5:
+        raise ValueError(f"expected a 5-D NDHWC tensor, got shape {tuple(x.shape)}")
+    if x.dtype == torch.float16 or x.dtype == torch.float64:
+        x = x.to(torch.float32)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"unsupported input dtype {x.dtype}")
+    if not x.is_cuda:
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("no CUDA device: the X3D path has no CPU implementation")
+            device = torch.device("cuda", torch.cuda.current_device())
+        x = x.to(device, non_blocking=True)
+    return x.contiguous()
+
+
+def _pad_channels(x: torch.Tensor, cs: int) -> torch.Tensor:
+    c = x.shape[-1]
+    if c == cs:
+        return x
+    out = torch.zeros(x.shape[:-1] + (cs,), dtype=x.dtype, device=x.device)
+    out[..., :c] = x
+    return out
+
+
+class PointwiseConv:
+    """Device-side state of one 1x1x1 conv (+ folded BN): fp32 [K,N] weights for the SIMT kernel
+    and packed bf16 [Npad,Kpad] weights for the tcgen05 kernel."""
+
+    def __init__(self, kernel: np.ndarray, scale, shift, device, bias=None):
+        k2 = kernel.reshape(kernel.shape[-2], kernel.shape[-1]).astype(np.float64)
+        K, N = k2.shape
+        self.K, self.N, self.Ks, self.Ns = K, N, _pad8(K), _pad8(N)
+        if scale is not None:
+            k2 = k2 * scale[None, :]
+        b = np.zeros(N, np.float64) if shift is None else np.asarray(shift, np.float64)
+        if bias is not None:
+            b = b + np.asarray(bias, np.float64)
+        wt = _pad_to(_pad_to(k2, 0, self.Ks), 1, self.Ns)
+        self.wt = _dev_f32(wt, device)
+        self.bias = _dev_f32(_pad_to(b, 0, self.Ns), device)
+        npad, kpad = (self.Ns + 15) // 16 * 16, (self.Ks + 63) // 64 * 64
+        wp = _pad_to(_pad_to(k2.T, 0, npad), 1, kpad)
+        self.wp = torch.from_numpy(np.ascontiguousarray(wp, dtype=np.float32)).to(device).to(
+            torch.bfloat16).contiguous()
+
+    def run(self, a: torch.Tensor, M: int, *, use_tc: bool, out_dtype=None, residual=None,
+            se=None, rows_per_clip=0, swish=False, relu=False, gather=None) -> torch.Tensor:
+        if use_tc and a.dtype == torch.bfloat16 and gather is None and \
+                (out_dtype is None or out_dtype == torch.bfloat16):
+            return ops.pw_tc_fwd(a, self.wp, self.bias, M=M, K=self.Ks, Nc=self.Ns,
+                                 residual=residual, se=se, rows_per_clip=rows_per_clip,
+                                 swish=swish, relu=relu)
+        return ops.pw_fwd(a, self.wt, self.bias, M=M, K=self.Ks, Nc=self.Ns, out_dtype=out_dtype,
+                          residual=residual, se=se, rows_per_clip=rows_per_clip, swish=swish,
+                          relu=relu, gather=gather)
+
+
+# Execution options shared by all layers of a process (the reference has no such switch; these
+# only choose between equivalent CUDA kernels).
+class Options:
+    pointwise = "tc"          # "tc": tcgen05 kernel for bf16 activations; "simt": CUDA-core GEMM
+
+
+def _use_tc() -> bool:
+    return Options.pointwise == "tc"
+
+
+# ======================================================================================
+class X3D_Stem(Layer):
+    """Reference `model.py:134-210`."""
+
+    def __init__(self, bn_cfg, regularizer=None, out_channels: int = 24,
+                 temp_filter_size: int = 5, in_channels: int = 3):
+        super().__init__(name="conv_1")
+        self.bn_momentum, self.bn_eps = bn_cfg.MOMENTUM, bn_cfg.EPS
+        self.out_channels, self.temp_filter_size = out_channels, temp_filter_size
+        self._add_conv("conv_s/kernel", (1, 3, 3, in_channels, out_channels))
+        self._add_conv("conv_t/kernel", (temp_filter_size, 1, 1, 1, out_channels),
+                       groups=out_channels)
+        self._add_bn("bn", out_channels)
+
+    def _prep(self, device):
+        key = (str(device),)
+        if key not in self._dev:
+            C, cs = self.out_channels, _pad8(self.out_channels)
+            s, t = self._fold_bn("bn", self.bn_eps)
+            ws = self._vars["conv_s/kernel"].reshape(27, C).astype(np.float64)
+            wt = self._vars["conv_t/kernel"].reshape(self.temp_filter_size, C).astype(np.float64) * s
+            self._dev[key] = {"ws": _dev_f32(_pad_to(ws, 1, cs), device),
+                              "wt": _dev_f32(_pad_to(wt, 1, cs), device),
+                              "bias": _dev_f32(_pad_to(t, 0, cs), device)}
+        return self._dev[key]
+
+    def _forward(self, x: torch.Tensor, out_dtype) -> torch.Tensor:
+        d = self._prep(x.device)
+        ops.Profiler.tag = "stem"
+        return ops.stem_fwd(x, d["ws"], d["wt"], d["bias"], out_dtype)
+
+    def call(self, input, training: bool = False):
+        self._no_training(training)
+        x = _as_device_clip(input, None)
+        return self._forward(x, x.dtype)[..., :self.out_channels]
+
+
+class AdaptiveAvgPool3D(Layer):
+    """Reference `model.py:457-492` (only the global (1,1,1) case does anything there too)."""
+
+    def __init__(self, spatial_out_shape=(1, 1, 1), data_format="channels_last", **kwargs):
+        super().__init__(name=kwargs.get("name"))
+        assert len(spatial_out_shape) == 3, "Please specify 3D shape"
+        assert data_format in ("channels_last", "channels_first")
+        self.data_format, self.out_shape = data_format, tuple(spatial_out_shape)
+
+    def call(self, input, training: bool = False):
+        x = _as_device_clip(input, None)
+        if self.data_format == "channels_first":
+            x = x.permute(0, 2, 3, 4, 1).contiguous()
+        m = ops.avgpool_fwd(x)                                   # [N, C] fp32
+        n, c = m.shape
+        o = self.out_shape
+        if self.data_format == "channels_last":
+            return m.reshape(-1, o[0], o[1], o[2], c)
+        return m.reshape(-1, c, o[0], o[1], o[2])
+
+
+class Bottleneck(Layer):
+    """Reference `model.py:212-320`."""
+
+    def __init__(self, channels: tuple, bn_cfg, regularizer=None, stride: int = 1,
+                 block_index: int = 0, se_ratio: float = 0.0625, temp_kernel_size: int = 3,
+                 in_channels: Optional[int] = None):
+        super().__init__()
+        if temp_kernel_size != 3:
+            raise NotImplementedError("only the 3x3x3 channelwise kernel is built")
+        self.block_index, self._bn_cfg = block_index, bn_cfg
+        self.inner, self.out_channels, self.stride = channels[0], channels[1], stride
+        self.in_channels = in_channels        # Keras infers it at first call; see _ensure_built
+        self.has_se = A.se_enabled(block_index)
+        self.se_width = A.round_width(self.inner, se_ratio) if self.has_se else 0
+        if in_channels is not None:
+            self._build(in_channels)
+
+    def _build(self, cin: int):
+        self.in_channels = cin
+        inner, cout = self.inner, self.out_channels
+        v = OrderedDict()
+        old, self._vars = self._vars, v
+        self._add_conv("a/kernel", (1, 1, 1, cin, inner))
+        self._add_bn("bn_a", inner)
+        self._add_conv("b/kernel", (3, 3, 3, 1, inner), groups=inner)
+        self._add_bn("bn_b", inner)
+        if self.has_se:
+            self._add_conv("se_fc1/kernel", (1, 1, 1, inner, self.se_width))
+            self._vars["se_fc1/bias"] = np.zeros(self.se_width, np.float32)
+            self._add_conv("se_fc2/kernel", (1, 1, 1, self.se_width, inner))
+            self._vars["se_fc2/bias"] = np.zeros(inner, np.float32)
+        self._add_conv("c/kernel", (1, 1, 1, inner, cout))
+        self._add_bn("bn_c", cout)
+        self._vars.update(old)
+
+    def _prep(self, device):
+        key = (str(device),)
+        if key not in self._dev:
+            eps = self._bn_cfg.EPS
+            ci = _pad8(self.inner)
+            sa, ta = self._fold_bn("bn_a", eps)
+            sb, tb = self._fold_bn("bn_b", eps)
+            sc, tc = self._fold_bn("bn_c", eps)
+            d = {"a": PointwiseConv(self._vars["a/kernel"], sa, ta, device),
+                 "c": PointwiseConv(self._vars["c/kernel"], sc, tc, device)}
+            wb = self._vars["b/kernel"].reshape(27, self.inner).astype(np.float64) * sb
+            d["wb"] = _dev_f32(_pad_to(wb, 1, ci), device)
+            d["bb"] = _dev_f32(_pad_to(tb, 0, ci), device)
+            if self.has_se:
+                w1 = self._vars["se_fc1/kernel"].reshape(self.inner, self.se_width)
+                w2 = self._vars["se_fc2/kernel"].reshape(self.se_width, self.inner)
+                d["w1"] = _dev_f32(_pad_to(w1, 0, ci), device)
+                d["b1"] = _dev_f32(self._vars["se_fc1/bias"], device)
+                d["w2"] = _dev_f32(_pad_to(w2, 1, ci), device)
+                d["b2"] = _dev_f32(_pad_to(self._vars["se_fc2/bias"], 0, ci), device)
+            self._dev[key] = d
+        return self._dev[key]
+
+    def _forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None,
+                 relu: bool = False) -> torch.Tensor:
+        """x: [N,T,H,W,pad8(cin)].  `residual`/`relu`: the ResBlock add + ReLU fused into c's epilogue."""
+        if self.in_channels is None:
+            raise RuntimeError("Bottleneck used before its input width is known")
+        d = self._prep(x.device)
+        N, T, H, W, _ = x.shape
+        ci = _pad8(self.inner)
+        tc = _use_tc()
+        ops.Profiler.tag = "a"
+        a = d["a"].run(x, N * T * H * W, use_tc=tc, relu=True).view(N, T, H, W, ci)
+        _, ph, _ = A.same_pad(H, 3, self.stride)
+        _, pw, _ = A.same_pad(W, 3, self.stride)
+        ops.Profiler.tag = "b"
+        b, partial = ops.dw_fwd(a, d["wb"], d["bb"], self.stride, ph, pw, self.has_se)
+        del a
+        _, _, Ho, Wo, _ = b.shape
+        se = None
+        if self.has_se:
+            ops.Profiler.tag = "se"
+            se = ops.se_mlp_fwd(partial, T * Ho * Wo, d["w1"], d["b1"], d["w2"], d["b2"])
+        ops.Profiler.tag = "c"
+        out = d["c"].run(b, N * T * Ho * Wo, use_tc=tc, se=se, rows_per_clip=T * Ho * Wo,
+                         swish=True, residual=residual, relu=relu)
+        return out.view(N, T, Ho, Wo, _pad8(self.out_channels))
+
+    def call(self, input, training: bool = False):
+        self._no_training(training)
+        x = _as_device_clip(input, None)
+        if self.in_channels is None:
+            self._build(x.shape[-1])
+        if x.shape[-1] != self.in_channels:
+            raise ValueError(f"expected {self.in_channels} input channels, got {x.shape[-1]}")
+        y = self._forward(_pad_channels(x, _pad8(self.in_channels)))
+        return y[..., :self.out_channels]
+
+
+class ResBlock(Layer):
+    """Reference `model.py:322-394`.  `_block_index` is the same process-global class counter."""
+
+    _block_index = 0
+
+    def __init__(self, channels: tuple, bn_cfg, regularizer=None, stride: int = 1,
+                 se_ratio: float = 0.0625, temp_kernel_size: int = 3):
+        super().__init__(name="ResBlock_%u" % ResBlock._block_index)
+        ResBlock._block_index += 1
+        self.in_channels, self.inner_channels, self.out_channels = channels
+        self._bn_cfg, self.stride = bn_cfg, stride
+        self.has_shortcut = self.in_channels != self.out_channels or stride != 1
+        if self.has_shortcut:
+            self._add_conv("residual/kernel", (1, 1, 1, self.in_channels, self.out_channels))
+            self._add_bn("bn_r", self.out_channels)
+        self.bottleneck = self._child("bottleneck", Bottleneck(
+            channels=channels[1:], stride=stride, bn_cfg=bn_cfg, regularizer=regularizer,
+            block_index=ResBlock._block_index, se_ratio=se_ratio,
+            temp_kernel_size=temp_kernel_size, in_channels=self.in_channels))
+
+    def _prep(self, device):
+        key = (str(device),)
+        if key not in self._dev:
+            d = {}
+            if self.has_shortcut:
+                s, t = self._fold_bn("bn_r", self._bn_cfg.EPS)
+                d["r"] = PointwiseConv(self._vars["residual/kernel"], s, t, device)
+            self._dev[key] = d
+        return self._dev[key]
+
+    def _forward(self, x: torch.Tensor) -> torch.Tensor:
+        d = self._prep(x.device)
+        N, T, H, W, _ = x.shape
+        if self.has_shortcut:
+            s = self.stride
+            Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+            ops.Profiler.tag = "shortcut"
+            res = d["r"].run(x, N * T * Ho * Wo, use_tc=False, gather=(T, Ho, Wo, H, W, s))
+        else:
+            res = x
+        return self.bottleneck._forward(x, residual=res, relu=True)
+
+    def call(self, input, training: bool = False):
+        self._no_training(training)
+        x = _as_device_clip(input, None)
+        if x.shape[-1] != self.in_channels:
+            raise ValueError(f"expected {self.in_channels} input channels, got {x.shape[-1]}")
+        y = self._forward(_pad_channels(x, _pad8(self.in_channels)))
+        return y[..., :self.out_channels]
+
+
+class ResStage(Layer):
+    """Reference `model.py:396-455`."""
+
+    _stage_index = 2
+
+    def __init__(self, in_channels: int, inner_channels: int, out_channels: int, depth: int,
+                 bn_cfg, regularizer=None, se_ratio: float = 0.0625, temp_kernel_size: int = 3):
+        super().__init__(name="res_stage_%u" % ResStage._stage_index)
+        ResStage._stage_index += 1
+        self._bn_cfg, self._inner_channels = bn_cfg, inner_channels
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.blocks: List[ResBlock] = []
+        for i in range(depth):
+            blk = ResBlock(bn_cfg=bn_cfg, se_ratio=se_ratio, regularizer=regularizer,
+                           temp_kernel_size=temp_kernel_size, stride=2 if i == 0 else 1,
+                           channels=(in_channels if i == 0 else out_channels, inner_channels,
+                                     out_channels))
+            # checkpoint path of the i-th layer of the inner K.Sequential `self.stage`
+            self.blocks.append(self._child(f"stage/layer_with_weights-{i}", blk))
+
+    def _forward(self, x):
+        for b in self.blocks:
+            x = b._forward(x)
+        return x
+
+    def call(self, input, training: bool = False):
+        self._no_training(training)
+        x = _as_device_clip(input, None)
+        y = self._forward(_pad_channels(x, _pad8(self.in_channels)))
+        return y[..., :self.out_channels]
+
+
+def reset_block_counters() -> None:
+    """Back to the fresh-process state of the reference's class counters (model.py:326,401)."""
+    ResBlock._block_index = 0
+    ResStage._stage_index = 2
+
+
+class _Conv5(Layer):
+    """`K.Sequential(name='conv_5')` of Conv3D + BN + ReLU (model.py:78-93)."""
+
+    def __init__(self, cin: int, cout: int, bn_cfg):
+        super().__init__(name="conv_5")
+        self.cin, self.cout, self._bn_cfg = cin, cout, bn_cfg
+        self._add_conv("layer_with_weights-0/kernel", (1, 1, 1, cin, cout))
+        self._add_bn("layer_with_weights-1", cout)
+
+    def _prep(self, device):
+        key = (str(device),)
+        if key not in self._dev:
+            s, t = self._fold_bn("layer_with_weights-1", self._bn_cfg.EPS)
+            self._dev[key] = PointwiseConv(self._vars["layer_with_weights-0/kernel"], s, t, device)
+        return self._dev[key]
+
+    def _forward(self, x):
+        N, T, H, W, _ = x.shape
+        ops.Profiler.tag = "conv5"
+        y = self._prep(x.device).run(x, N * T * H * W, use_tc=_use_tc(), relu=True)
+        return y.view(N, T, H, W, _pad8(self.cout))
+
+
+class _Dense(Layer):
+    def __init__(self, name, key_shape, bias: bool):
+        super().__init__(name=name)
+        if len(key_shape) == 5:
+            self._add_conv("kernel", key_shape)
+        else:
+            self._vars["kernel"] = _glorot(self._rng(), key_shape, key_shape[0], key_shape[1])
+        if bias:
+            self._vars["bias"] = np.zeros(key_shape[-1], np.float32)
+
+    def _prep(self, device):
+        key = (str(device),)
+        if key not in self._dev:
+            self._dev[key] = PointwiseConv(self._vars["kernel"], None, None, device,
+                                           bias=self._vars.get("bias"))
+        return self._dev[key]
+
+
+class X3D(Layer):
+    """Reference `model.py:8-132`.
+
+    `dtype`: None (default) = compute in the dtype of the clips passed to `call` (float32 ->
+    fp32 kernels, bfloat16 -> bf16 storage / fp32 accumulate); "bfloat16" = store activations in
+    bf16 whatever the input dtype (float32 clips are read directly by the stem)."""
+
+    def __init__(self, cfg, dtype: Optional[str] = None, device=None, use_cuda_graph: bool = True):
+        super().__init__(name="X3D")
+        self.cfg = cfg
+        self.num_classes = cfg.NETWORK.NUM_CLASSES
+        self._bn_cfg = cfg.NETWORK.BN
+        self._num_preds = cfg.TEST.NUM_TEMPORAL_VIEWS * cfg.TEST.NUM_SPATIAL_CROPS
+        self._arch = A.build_arch(cfg, first_block_index=ResBlock._block_index + 1)
+        self._conv1_dim = self._arch.stem_channels
+        self._dtype = {None: None, "float32": torch.float32, "bfloat16": torch.bfloat16,
+                       "bf16": torch.bfloat16, "fp32": torch.float32}[dtype]
+        self._device = torch.device(device) if device is not None else None
+        self._use_graph = use_cuda_graph
+        self._graphs: Dict[tuple, tuple] = {}
+        self.last_logits: Optional[torch.Tensor] = None
+
+        self.conv1 = self._child("conv1", X3D_Stem(
+            regularizer=None, bn_cfg=cfg.NETWORK.BN, out_channels=self._conv1_dim,
+            temp_filter_size=cfg.NETWORK.C1_TEMP_FILTER,
+            in_channels=cfg.DATA.NUM_INPUT_CHANNELS))
+        self.stages: List[ResStage] = []
+        for s, (depth, cin, inner, cout) in enumerate(self._arch.stage_dims):
+            st = ResStage(in_channels=cin, inner_channels=inner, out_channels=cout, depth=depth,
+                          bn_cfg=self._bn_cfg, regularizer=None)
+            self.stages.append(self._child(f"stages/{s}", st))
+        last_out = self._arch.stage_dims[-1][3]
+        c5 = self.stages[-1]._inner_channels
+        self.conv5 = self._child("conv5", _Conv5(last_out, c5, self._bn_cfg))
+        self.pool5 = AdaptiveAvgPool3D(name="pool_5")
+        self.fc1 = self._child("fc1", _Dense("fc_1", (1, 1, 1, c5, 2048), bias=False))
+        self.dropout_rate = cfg.NETWORK.DROPOUT_RATE
+        self.fc2 = self._child("fc2", _Dense("fc_2", (2048, self.num_classes), bias=True))
+
+    # ---- weights
+    def set_weights_dict(self, weights, prefix: str = "", strict: bool = True):
+        self._graphs.clear()
+        return super().set_weights_dict(weights, prefix, strict)
+
+    def load_weights(self, filepath: str, verify: bool = True) -> _LoadStatus:
+        """Restore from a TF-format checkpoint prefix (`train.py:137-143`, `eval.py:78-81`)."""
+        names = set(self.named_variables())
+        got = tf_bundle.load_model_variables(filepath, verify=verify)
+        missing = self.set_weights_dict(got, strict=False)
+        return _LoadStatus(missing, sorted(set(got) - names))
+
+    def save_weights(self, filepath: str) -> None:
+        tf_bundle.write_bundle(filepath, dict(self.named_variables()))
+
+    # ---- forward
+    def _forward(self, x: torch.Tensor, training: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+        act_dtype = self._dtype or x.dtype
+        out = self.conv1._forward(x, act_dtype)
+        for st in self.stages:
+            out = st._forward(out)
+        out = self.conv5._forward(out)
+        ops.Profiler.tag = "head"
+        pooled = ops.avgpool_fwd(out)                                   # [N, C5s] fp32
+        N = pooled.shape[0]
+        f1 = self.fc1._prep(x.device)
+        h = ops.pw_fwd(pooled, f1.wt, None, M=N, K=f1.Ks, Nc=f1.Ns, relu=True)
+        f2 = self.fc2._prep(x.device)
+        logits_p = ops.pw_fwd(h, f2.wt, f2.bias, M=N, K=f2.Ks, Nc=f2.Ns)
+        logits = logits_p if f2.Ns == self.num_classes else \
+            logits_p[:, :self.num_classes].contiguous()
+        probs = ops.softmax_viewmean_fwd(logits, 1 if training else self._num_preds)
+        return probs, logits
+
+    def call(self, input, training: bool = False):
+        self._no_training(training)
+        x = _as_device_clip(input, self._device)
+        if x.shape[-1] != self.cfg.DATA.NUM_INPUT_CHANNELS:
+            raise ValueError(f"expected {self.cfg.DATA.NUM_INPUT_CHANNELS} input channels")
+        if x.shape[0] % self._num_preds != 0:
+            raise ValueError(f"batch {x.shape[0]} must be a multiple of "
+                             f"NUM_TEMPORAL_VIEWS*NUM_SPATIAL_CROPS = {self._num_preds}")
+        if not self._use_graph:
+            probs, self.last_logits = self._forward(x, training)
+            return probs
+        key = (tuple(x.shape), x.dtype, str(x.device), Options.pointwise)
+        if key not in self._graphs:
+            # first call with this shape: eager run (also warms lazy CUDA state), then capture
+            probs, logits = self._forward(x, training)
+            torch.cuda.current_stream().synchronize()
+            static_in = x.clone()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                s_probs, s_logits = self._forward(static_in, training)
+            self._graphs[key] = (g, static_in, s_probs, s_logits)
+        g, static_in, s_probs, s_logits = self._graphs[key]
+        if x.data_ptr() != static_in.data_ptr():
+            static_in.copy_(x, non_blocking=True)
+        g.replay()
+        self.last_logits = s_logits
+        return s_probs
+
+    def static_input(self, shape, dtype=torch.bfloat16):
+        """The captured graph's input buffer for `shape` (fill it in place and pass it to
+        `call` to skip the staging copy).  None until the first call with that shape."""
+        for (shp, dt, _, _), (_, static_in, _, _) in self._graphs.items():
+            if tuple(shp) == tuple(shape) and dt == dtype:
+                return static_in
+        return None
+
+    def summary(self, input_shape) -> str:
+        """Keras-style table (`model.py:129-132`, dumps in `models/*/X3D_*.txt`)."""
+        T, H, W, _ = input_shape
+        plan = A.plan_shapes(self._arch, T, H, W)
+        rows = [("input_1 (InputLayer)", f"[(None, {T}, {H}, {W}, {input_shape[3]})]", 0),
+                ("conv_1 (X3D_Stem)", f"(None, {T}, {plan.stem.H}, {plan.stem.W}, {self._conv1_dim})",
+                 self.conv1.count_params())]
+        for s, st in enumerate(self.stages):
+            lv = plan.stages[s]
+            rows.append((f"res_stage_{s + 2} (ResStage)",
+                         f"(None, {T}, {lv.H}, {lv.W}, {st.out_channels})", st.count_params()))
+        lv = plan.stages[-1]
+        rows += [("conv_5 (Sequential)", f"(None, {T}, {lv.H}, {lv.W}, {self.conv5.cout})",
+                  self.conv5.count_params()),
+                 ("pool_5 (AdaptiveAvgPool3D)", f"(None, 1, 1, 1, {self.conv5.cout})", 0),
+                 ("fc_1 (Conv3D)", "(None, 1, 1, 1, 2048)", self.fc1.count_params()),
+                 ("dropout (Dropout)", "(None, 1, 1, 1, 2048)", 0),
+                 ("fc_2 (Dense)", f"(None, 1, 1, 1, {self.num_classes})", self.fc2.count_params())]
+        total = self.count_params()
+        nontrain = sum(int(v.size) for k, v in self.named_variables().items()
+                       if not A.is_trainable(k))
+        lines = ['Model: "X3D"', "_" * 65, f"{'Layer (type)':<29}{'Output Shape':<26}Param #",
+                 "=" * 65]
+        for name, shape, n in rows:
+            lines += [f"{name:<29}{shape:<26}{n}", "_" * 65]
+        lines[-1] = "=" * 65
+        lines += [f"Total params: {total:,}", f"Trainable params: {total - nontrain:,}",
+                  f"Non-trainable params: {nontrain:,}", "_" * 65]
+        text = "\n".join(lines)
+        print(text)
+        return text

@@ -1,0 +1,186 @@
+"""Thin tensor-level wrappers over the C ABI (`include/x3d_b200.h`).
+
+PyTorch is used only to own device memory and the CUDA stream; every function below launches
+one hand-written kernel through ctypes and returns the output tensor.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import X3D_BF16, X3D_F32, PwArgs, PwTcArgs, check, lib
+
+
+class Profiler:
+    """Optional per-launch timing (CUDA events on the launching stream) used by bench.py to
+    attribute time to kernel classes.  Off by default; never changes what is launched."""
+    enabled = False
+    tag = ""
+    records: list = []
+    launches = 0
+
+    @classmethod
+    def start(cls):
+        cls.enabled, cls.records, cls.launches = True, [], 0
+
+    @classmethod
+    def stop(cls):
+        cls.enabled = False
+        torch.cuda.synchronize()
+        out = [(tag, name, e0.elapsed_time(e1)) for tag, name, e0, e1 in cls.records]
+        cls.records = []
+        return out
+
+
+def _launch(name: str, fn) -> None:
+    Profiler.launches += 1
+    if Profiler.enabled:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        status = fn()
+        e1.record()
+        Profiler.records.append((Profiler.tag, name, e0, e1))
+    else:
+        status = fn()
+    check(status, name)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return X3D_F32
+    if t.dtype == torch.bfloat16:
+        return X3D_BF16
+    raise TypeError(f"unsupported activation dtype {t.dtype} (float32 or bfloat16)")
+
+
+def _torch_dt(code: int):
+    return torch.float32 if code == X3D_F32 else torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stem_fwd(x: torch.Tensor, ws: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor,
+             out_dtype: torch.dtype) -> torch.Tensor:
+    _req(x, "x")
+    N, T, H, W, ci = x.shape
+    if ci != 3:
+        raise ValueError("stem input must have 3 channels")
+    C = bias.numel()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty((N, T, Ho, Wo, C), dtype=out_dtype, device=x.device)
+    _launch("x3d_stem_fwd", lambda: lib().x3d_stem_fwd(x.data_ptr(), _dt(x), ws.data_ptr(), wt.data_ptr(), bias.data_ptr(),
+                             out.data_ptr(), _dt(out), N, T, H, W, C, wt.shape[0], _stream()))
+    return out
+
+
+def pw_fwd(a: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, M: int, K: int,
+           Nc: int, out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+           residual: Optional[torch.Tensor] = None, se: Optional[torch.Tensor] = None,
+           rows_per_clip: int = 0, swish: bool = False, relu: bool = False,
+           gather: Optional[Tuple[int, int, int, int, int, int]] = None) -> torch.Tensor:
+    """Generic SIMT pointwise GEMM.  `a` is viewed as [*, lda=K]; `gather`=(T,Ho,Wo,Hi,Wi,stride)
+    selects strided input pixels (shortcut conv)."""
+    _req(a, "a")
+    if out is None:
+        out = torch.empty((M, Nc), dtype=out_dtype or a.dtype, device=a.device)
+    args = PwArgs()
+    args.A, args.Wt, args.bias = a.data_ptr(), wt.data_ptr(), _ptr(bias)
+    args.R, args.se, args.D = _ptr(residual), _ptr(se), out.data_ptr()
+    args.M, args.K, args.Nc = M, K, Nc
+    args.lda, args.ldw, args.ldr, args.ldd = K, wt.shape[1], Nc, Nc
+    args.rows_per_clip = rows_per_clip
+    args.a_dtype, args.d_dtype = _dt(a), _dt(out)
+    args.swish, args.relu = int(swish), int(relu)
+    if gather is not None:
+        args.gather = 1
+        args.T, args.Ho, args.Wo, args.Hi, args.Wi, args.stride = gather
+    _launch("x3d_pw_fwd", lambda: lib().x3d_pw_fwd(args, _stream()))
+    return out
+
+
+def pw_tc_fwd(a: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], *, M: int, K: int,
+              Nc: int, out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+              se: Optional[torch.Tensor] = None, rows_per_clip: int = 0, swish: bool = False,
+              relu: bool = False) -> torch.Tensor:
+    """tcgen05 pointwise GEMM (bf16).  `wp` is the packed [Npad, Kpad] bf16 weight."""
+    _req(a, "a")
+    if a.dtype != torch.bfloat16:
+        raise TypeError("pw_tc_fwd needs bf16 activations")
+    if out is None:
+        out = torch.empty((M, Nc), dtype=torch.bfloat16, device=a.device)
+    args = PwTcArgs()
+    args.A, args.Wp, args.bias = a.data_ptr(), wp.data_ptr(), _ptr(bias)
+    args.R, args.se, args.D = _ptr(residual), _ptr(se), out.data_ptr()
+    args.M, args.K, args.Nc = M, K, Nc
+    args.lda, args.ldr, args.ldd = K, Nc, Nc
+    args.Npad, args.Kpad = wp.shape
+    args.rows_per_clip = rows_per_clip
+    args.swish, args.relu = int(swish), int(relu)
+    _launch("x3d_pw_tc_fwd", lambda: lib().x3d_pw_tc_fwd(args, _stream()))
+    return out
+
+
+def dw_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: int, pad_h: int,
+           pad_w: int, want_se: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    _req(x, "x")
+    N, T, H, W, C = x.shape
+    Ho, Wo = -(-H // stride), -(-W // stride)
+    out = torch.empty((N, T, Ho, Wo, C), dtype=x.dtype, device=x.device)
+    partial = None
+    if want_se:
+        nblk = lib().x3d_dw_partial_blocks(T, H, W, C, stride)
+        if nblk <= 0:
+            raise _lib.X3DLibError("x3d_dw_partial_blocks rejected the shape")
+        partial = torch.empty((N, nblk, C), dtype=torch.float32, device=x.device)
+    _launch("x3d_dw3x3x3_fwd", lambda: lib().x3d_dw3x3x3_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                _ptr(partial), N, T, H, W, C, stride, pad_h, pad_w, _dt(x),
+                                _stream()))
+    return out, partial
+
+
+def se_mlp_fwd(partial: torch.Tensor, count: int, w1: torch.Tensor, b1: torch.Tensor,
+               w2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
+    N, nblk, C = partial.shape
+    scale = torch.empty((N, C), dtype=torch.float32, device=partial.device)
+    _launch("x3d_se_mlp_fwd", lambda: lib().x3d_se_mlp_fwd(partial.data_ptr(), nblk, 1.0 / float(count), w1.data_ptr(),
+                               b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), scale.data_ptr(),
+                               N, C, w1.shape[1], _stream()))
+    return scale
+
+
+def avgpool_fwd(x: torch.Tensor) -> torch.Tensor:
+    """[N, ..., C] -> [N, C] fp32 mean over all middle positions."""
+    _req(x, "x")
+    N, C = x.shape[0], x.shape[-1]
+    P = x.numel() // (N * C)
+    out = torch.empty((N, C), dtype=torch.float32, device=x.device)
+    _launch("x3d_avgpool_fwd", lambda: lib().x3d_avgpool_fwd(x.data_ptr(), out.data_ptr(), N, P, C, _dt(x), _stream()))
+    return out
+
+
+def softmax_viewmean_fwd(logits: torch.Tensor, num_preds: int) -> torch.Tensor:
+    _req(logits, "logits")
+    N, ncls = logits.shape
+    if N % num_preds:
+        raise ValueError(f"batch {N} is not a multiple of num_preds {num_preds}")
+    probs = torch.empty((N // num_preds, ncls), dtype=torch.float32, device=logits.device)
+    _launch("x3d_softmax_viewmean_fwd", lambda: lib().x3d_softmax_viewmean_fwd(logits.data_ptr(), probs.data_ptr(), N, ncls, num_preds,
+                                         _stream()))
+    return probs
