@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "tma_common.cuh"
 
 namespace x3d {
 
@@ -37,6 +38,34 @@ struct CrcTables {
       for (int s = 1; s < 8; ++s) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xff];
   }
 };
+
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static int g_sms = -1, g_smem = 0, g_major = 0;
+static void query_device() {
+  if (g_sms >= 0) return;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { g_sms = 0; return; }
+  cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&g_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&g_major, cudaDevAttrComputeCapabilityMajor, dev);
+}
+int device_sm_count() { query_device(); return g_sms; }
+int device_max_smem() { query_device(); return g_smem; }
+bool device_is_sm100() { query_device(); return g_major == 10; }
 
 }  // namespace x3d
 

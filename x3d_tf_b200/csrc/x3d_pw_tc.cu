@@ -14,76 +14,19 @@
 //
 // Reference call sites replaced: Bottleneck.a/bn_a/relu (model.py:306-308), Bottleneck.c/bn_c +
 // ResBlock add/relu (model.py:317-318,389-392), conv5 (model.py:117).
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tma_common.cuh"
 
 namespace x3d {
 namespace tc {
 
 constexpr int kBlockM = 128, kBlockK = 64, kStageBytes = kBlockM * kBlockK * 2;
-constexpr uint32_t kSpinLimit = 1u << 24;
+using namespace ptx;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > kSpinLimit) __trap();      // a lost arrival must fail the launch, not hang the GPU
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void tcgen05_before_sync() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
 __device__ __forceinline__ void tcgen05_after_sync() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .b32 r;\n\t.reg .pred p;\n\t"
-      "elect.sync r|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc]
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
@@ -366,29 +309,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------ host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) ==
-            cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
 static bool make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer,
                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
-  EncodeTiledFn enc = get_encode();
+  EncodeTiledFn enc = tensor_map_encoder();
   if (!enc) return false;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_stride_bytes};
@@ -399,8 +322,6 @@ static bool make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int g_num_sms = 0;
-static int g_max_smem = 0;
 
 }  // namespace tc
 }  // namespace x3d
@@ -419,22 +340,14 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   X3D_REQUIRE(!a->se || a->rows_per_clip > 0, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: rows_per_clip missing");
   X3D_REQUIRE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->Wp) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(a->D) & 15) == 0, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: pointers must be 16-byte aligned");
-  if (tc::g_num_sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("x3d_pw_tc_fwd: no CUDA device"); return X3D_ERR_NO_DEVICE; }
-    cudaDeviceGetAttribute(&tc::g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&tc::g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    int major = 0;
-    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-    if (major != 10) { tc::g_num_sms = 0; set_error("x3d_pw_tc_fwd: device is not sm_100"); return X3D_ERR_NO_DEVICE; }
-  }
+  X3D_REQUIRE(device_sm_count() > 0 && device_is_sm100(), X3D_ERR_NO_DEVICE, "x3d_pw_tc_fwd: needs an sm_100 device");
   // N tiling: fewest tiles with NT <= 256 whose resident weight slice leaves >= 3 A stages.
   const int kc_n = a->Kpad / 64;
   const int k16_total = (a->K + 15) / 16;
   const int KC = (k16_total + 3) / 4;                 // chunks that actually hold data
   const int k16_last = k16_total - (KC - 1) * 4;
   (void)kc_n;
-  const int budget = tc::g_max_smem - 1024 /*align*/ - 1024 /*bias*/ - 512 /*barriers*/;
+  const int budget = device_max_smem() - 1024 /*align*/ - 1024 /*bias*/ - 512 /*barriers*/;
   int n_tiles = (a->Npad + 255) / 256;
   int NT = 0, stages = 0;
   for (;; ++n_tiles) {
@@ -452,7 +365,7 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   X3D_REQUIRE(tmem_cols <= 512, X3D_ERR_UNSUPPORTED, "x3d_pw_tc_fwd: NT=%d needs too much TMEM", NT);
 
   CUtensorMap tmA, tmW;
-  X3D_REQUIRE(tc::get_encode() != nullptr, X3D_ERR_NO_DEVICE, "x3d_pw_tc_fwd: cuTensorMapEncodeTiled unavailable");
+  X3D_REQUIRE(tensor_map_encoder() != nullptr, X3D_ERR_NO_DEVICE, "x3d_pw_tc_fwd: cuTensorMapEncodeTiled unavailable");
   X3D_REQUIRE(tc::make_map_2d(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, 64, 128),
               X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: tensor map for A failed (K=%d M=%ld lda=%d)", a->K, (long)a->M, a->lda);
   // The weight box may reach past Npad rows on the last tile: TMA zero-fills.
@@ -467,7 +380,7 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
 
   const size_t smem = 1024 + (size_t)KC * NT * 128 + (size_t)stages * tc::kStageBytes + 1024 + 512;
   const long num_tiles = (a->M + tc::kBlockM - 1) / tc::kBlockM;
-  int gx = tc::g_num_sms / n_tiles;
+  int gx = device_sm_count() / n_tiles;
   if (gx < 1) gx = 1;
   if (gx > num_tiles) gx = (int)num_tiles;
   dim3 grid(gx, n_tiles);

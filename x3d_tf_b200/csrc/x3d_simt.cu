@@ -1,8 +1,7 @@
 // CUDA-core (SIMT) kernels of the X3D forward path for sm_100a:
-//   stem (fused conv_s + conv_t + BN + ReLU), channelwise 3x3x3 stencil (+BN, +SE partial sums),
-//   SE MLP, global average pool, softmax + view mean, and the generic fp32-accumulate pointwise
+//   stem (fused conv_s + conv_t + BN + ReLU), SE MLP, global average pool, softmax + view mean, and the generic fp32-accumulate pointwise
 //   GEMM used by the fp32 path, the strided shortcut conv and the head.
-// The bf16 tensor-core pointwise GEMM lives in x3d_pw_tc.cu.
+// The bf16 tensor-core pointwise GEMM lives in x3d_pw_tc.cu, the channelwise stencil in x3d_dw_tma.cu.
 #include "common.cuh"
 
 namespace x3d {
@@ -110,109 +109,6 @@ stem_kernel(const TI* __restrict__ in, const float* __restrict__ ws, const float
       }
     }
     __syncthreads();
-  }
-}
-
-// =====================================================================================
-// Channelwise 3x3x3 stencil + BN (+ SE partial sums).
-// A thread owns one channel pair (its 27 taps x 2 channels stay in registers for the whole
-// kernel) and computes register blocks of 2 frames x SW output columns: 4 input frames x 3 rows
-// x ((SW-1)*S+3) columns are loaded once each and reused across the 2x3 temporal/column taps.
-// blockDim.x = (C/2) * k_slots: `slot` selects which block of a group of k_slots the thread works
-// on, so warps read contiguous channel runs (coalesced) with no idle lanes.
-template <typename T, int S, int SW>
-__global__ void __launch_bounds__(384)
-dw3x3x3_kernel(const T* __restrict__ in, const float* __restrict__ w,
-               const float* __restrict__ bias, T* __restrict__ out, float* __restrict__ partial,
-               int Tn, int H, int W, int Ho, int Wo, int Cs, int pad_h, int pad_w, int strips_w,
-               int total_strips, int k_slots) {
-  constexpr int NCOL = (SW - 1) * S + 3;
-  extern __shared__ float s_red[];                 // [k_slots][Cs] when partial != nullptr
-  const int C2 = Cs >> 1;
-  const int tid = threadIdx.x;
-  const int slot = tid / C2, cp = tid - slot * C2;
-  const bool on = slot < k_slots;
-  const int n = blockIdx.y;
-  const int c = cp * 2;
-
-  float2 wr[27];
-#pragma unroll
-  for (int i = 0; i < 27; ++i) wr[i] = ld2(w + i * Cs + c);
-  const float2 b = ld2(bias + c);
-  float2 ssum = make_float2(0.f, 0.f);
-
-  const T* in_n = in + (long)n * Tn * H * W * Cs;
-  T* out_n = out + (long)n * Tn * Ho * Wo * Cs;
-
-  if (on) {
-    for (int s = blockIdx.x * k_slots + slot; s < total_strips; s += gridDim.x * k_slots) {
-      const int wsi = s % strips_w;
-      const int r = s / strips_w;
-      const int ho = r % Ho, tp = r / Ho;
-      const int t0 = tp * 2, wo0 = wsi * SW;
-      const int wi0 = wo0 * S - pad_w;
-      float2 acc[2][SW];
-#pragma unroll
-      for (int f = 0; f < 2; ++f)
-#pragma unroll
-        for (int j = 0; j < SW; ++j) acc[f][j] = make_float2(0.f, 0.f);
-
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int ti = t0 - 1 + i;
-        if (ti < 0 || ti >= Tn) continue;
-#pragma unroll
-        for (int dh = 0; dh < 3; ++dh) {
-          const int hi = ho * S - pad_h + dh;
-          if (hi < 0 || hi >= H) continue;
-          const T* row = in_n + ((long)(ti * H + hi) * W) * Cs + c;
-          float2 v[NCOL];
-#pragma unroll
-          for (int j = 0; j < NCOL; ++j) {
-            const int wi = wi0 + j;
-            v[j] = (wi >= 0 && wi < W) ? ld2(row + (long)wi * Cs) : make_float2(0.f, 0.f);
-          }
-#pragma unroll
-          for (int f = 0; f < 2; ++f) {
-            const int dt = i - f;            // input frame ti is tap dt of output frame t0+f
-            if (dt < 0 || dt > 2) continue;  // resolved at compile time (i, f unrolled)
-#pragma unroll
-            for (int dw = 0; dw < 3; ++dw) {
-              const float2 wg = wr[(dt * 3 + dh) * 3 + dw];
-#pragma unroll
-              for (int j = 0; j < SW; ++j) acc[f][j] = fma2(v[j * S + dw], wg, acc[f][j]);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        const int t = t0 + f;
-        if (t >= Tn) continue;
-        T* orow = out_n + ((long)(t * Ho + ho) * Wo) * Cs + c;
-#pragma unroll
-        for (int j = 0; j < SW; ++j) {
-          const int wo = wo0 + j;
-          if (wo >= Wo) continue;
-          float2 y = make_float2(acc[f][j].x + b.x, acc[f][j].y + b.y);
-          st2(orow + (long)wo * Cs, y);
-          ssum.x += y.x;
-          ssum.y += y.y;
-        }
-      }
-    }
-  }
-  if (partial != nullptr) {
-    if (on) {
-      s_red[slot * Cs + c] = ssum.x;
-      s_red[slot * Cs + c + 1] = ssum.y;
-    }
-    __syncthreads();
-    if (tid < Cs) {
-      float a = 0.f;
-      for (int k = 0; k < k_slots; ++k) a += s_red[k * Cs + tid];
-      partial[((long)n * gridDim.x + blockIdx.x) * Cs + tid] = a;
-    }
   }
 }
 
@@ -429,46 +325,6 @@ pw_gemm_kernel(const PwParams p) {
 // --------------------------------------------------------------------------- host side
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
-template <typename T, int STRIDE, int SW>
-static int launch_dw(const void* in, const float* w, const float* bias, void* out,
-                     float* partial, int N, int Tn, int H, int W, int Ho, int Wo, int C,
-                     int pad_h, int pad_w, int nblk, cudaStream_t st) {
-  const int C2 = C / 2;
-  const int k_slots = max(1, 256 / C2);
-  const int threads = ((C2 * k_slots + 31) / 32) * 32;
-  const int strips_w = (Wo + SW - 1) / SW;
-  const int total = ((Tn + 1) / 2) * Ho * strips_w;
-  const size_t smem = partial ? sizeof(float) * k_slots * C : 0;
-  dim3 grid(nblk, N);
-  dw3x3x3_kernel<T, STRIDE, SW><<<grid, threads, smem, st>>>(
-      static_cast<const T*>(in), w, bias, static_cast<T*>(out), partial, Tn, H, W, Ho, Wo, C,
-      pad_h, pad_w, strips_w, total, k_slots);
-  return check_launch("x3d_dw3x3x3_fwd");
-}
-
-static int dw_strip_width(int Wo, int stride) {
-  // candidate widths compiled in: stride 1 -> {4,7,8}; stride 2 -> {4}
-  if (stride == 2) return 4;
-  int best = 8, best_cost = ((Wo + 7) / 8) * 8;
-  const int cand[2] = {7, 4};
-  for (int k = 0; k < 2; ++k) {
-    const int cost = ((Wo + cand[k] - 1) / cand[k]) * cand[k];
-    if (cost < best_cost) { best = cand[k]; best_cost = cost; }
-  }
-  return best;
-}
-
-static int dw_blocks(int Tn, int H, int W, int C, int stride) {
-  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
-  const int SW = dw_strip_width(Wo, stride);
-  const int strips_w = (Wo + SW - 1) / SW;
-  const int total = ((Tn + 1) / 2) * Ho * strips_w;
-  const int k_slots = max(1, 256 / (C / 2));
-  // aim at ~4 register blocks per thread, at most 256 partial rows per clip
-  int nblk = (total + k_slots * 4 - 1) / (k_slots * 4);
-  return max(1, min(nblk, 256));
-}
-
 }  // namespace x3d
 
 using namespace x3d;
@@ -498,41 +354,6 @@ int x3d_stem_fwd(const void* in, int in_dtype, const float* ws, const float* wt,
   else X3D_REQUIRE(false, X3D_ERR_INVALID_ARG, "x3d_stem_fwd: bad dtype %d/%d", in_dtype, out_dtype);
 #undef X3D_STEM
   return check_launch("x3d_stem_fwd");
-}
-
-int x3d_dw_partial_blocks(int T, int H, int W, int C, int stride) {
-  if (T <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 || (stride != 1 && stride != 2)) return 0;
-  return dw_blocks(T, H, W, C, stride);
-}
-
-int x3d_dw3x3x3_fwd(const void* in, const float* w, const float* bias, void* out,
-                    float* se_partial, int N, int T, int H, int W, int C, int stride, int pad_h,
-                    int pad_w, int dtype, void* stream) {
-  X3D_REQUIRE(in && w && bias && out, X3D_ERR_INVALID_ARG, "x3d_dw3x3x3_fwd: null pointer");
-  X3D_REQUIRE(C > 0 && C % 8 == 0, X3D_ERR_INVALID_ARG, "x3d_dw3x3x3_fwd: C=%d not a multiple of 8", C);
-  X3D_REQUIRE(C / 2 <= 384, X3D_ERR_UNSUPPORTED, "x3d_dw3x3x3_fwd: C=%d > 768", C);
-  X3D_REQUIRE(stride == 1 || stride == 2, X3D_ERR_UNSUPPORTED, "x3d_dw3x3x3_fwd: stride %d", stride);
-  X3D_REQUIRE(N > 0 && N <= 65535 && T > 0 && H > 0 && W > 0, X3D_ERR_INVALID_ARG, "x3d_dw3x3x3_fwd: bad extent");
-  X3D_REQUIRE(pad_h >= 0 && pad_h <= 1 && pad_w >= 0 && pad_w <= 1, X3D_ERR_INVALID_ARG, "x3d_dw3x3x3_fwd: pad_before must be 0 or 1");
-  X3D_REQUIRE(dtype == X3D_F32 || dtype == X3D_BF16, X3D_ERR_INVALID_ARG, "x3d_dw3x3x3_fwd: dtype %d", dtype);
-  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
-  const int nblk = dw_blocks(T, H, W, C, stride);
-  const int SW = dw_strip_width(Wo, stride);
-  cudaStream_t st = S(stream);
-#define X3D_DW(TT, ST, SWW) \
-  return launch_dw<TT, ST, SWW>(in, w, bias, out, se_partial, N, T, H, W, Ho, Wo, C, pad_h, pad_w, nblk, st)
-  if (dtype == X3D_BF16) {
-    if (stride == 2) X3D_DW(bf16, 2, 4);
-    if (SW == 8) X3D_DW(bf16, 1, 8);
-    if (SW == 7) X3D_DW(bf16, 1, 7);
-    X3D_DW(bf16, 1, 4);
-  } else {
-    if (stride == 2) X3D_DW(float, 2, 4);
-    if (SW == 8) X3D_DW(float, 1, 8);
-    if (SW == 7) X3D_DW(float, 1, 7);
-    X3D_DW(float, 1, 4);
-  }
-#undef X3D_DW
 }
 
 int x3d_se_mlp_fwd(const float* partial, int nblk, float inv_count, const float* w1,
