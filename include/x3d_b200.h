@@ -90,8 +90,9 @@ int x3d_pw_fwd(const x3d_pw_args* args, void* stream);
  * fixed-order partial sums (deterministic; no atomics):
  *   in  [N,T,H,W,C]; w [27,C] fp32 (dt,dh,dw major; BN scale folded); bias [C] fp32
  *   out [N,T,Ho,Wo,C], Ho=ceil(H/s), Wo=ceil(W/s)
- *   se_partial [N, nblk, C] fp32 with nblk = x3d_dw_partial_blocks(...) */
-int x3d_dw_partial_blocks(int T, int H, int W, int C, int stride);
+ *   se_partial [N, nblk, C] fp32 with nblk = x3d_dw_partial_blocks(...) (one row per spatial tile
+ *   of the launch; depends on the shape and dtype only) */
+int x3d_dw_partial_blocks(int T, int H, int W, int C, int stride, int dtype);
 int x3d_dw3x3x3_fwd(const void* in, const float* w, const float* bias, void* out,
                     float* se_partial, int N, int T, int H, int W, int C, int stride,
                     int pad_h, int pad_w, int dtype, void* stream);

@@ -57,8 +57,8 @@ def test_argument_validation_without_gpu():
     h = _lib.lib()
     assert h.x3d_dw3x3x3_fwd(None, None, None, None, None, 1, 1, 1, 1, 8, 1, 0, 0, 0, None) == -1
     assert b"null" in h.x3d_last_error()
-    assert h.x3d_dw_partial_blocks(16, 56, 56, 56, 1) > 0
-    assert h.x3d_dw_partial_blocks(16, 56, 56, 54, 1) == 0        # C not a multiple of 8
+    assert h.x3d_dw_partial_blocks(16, 56, 56, 56, 1, 1) == 49        # 7x7 tiles of 8x8
+    assert h.x3d_dw_partial_blocks(16, 56, 56, 54, 1, 1) == 0     # C not a multiple of 8
     assert h.x3d_softmax_viewmean_fwd(1, 1, 7, 400, 2, None) == -1 and b"multiple" in h.x3d_last_error()
 
 

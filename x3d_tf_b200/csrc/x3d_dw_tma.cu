@@ -65,7 +65,7 @@ template <> struct Pack<bf16> {
 };
 
 template <typename T, int S, int SW, int CH>
-__global__ void __launch_bounds__(288)
+__global__ void __launch_bounds__(224, 2)
 dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
               const Params p) {
   constexpr int BW = (SW - 1) * S + 3;
@@ -82,6 +82,9 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
   const uint32_t ring_s = smem_s + 128;                        // input ring  [kSlots][slot_bytes]
   const uint32_t stage_s = ring_s + kSlots * p.slot_bytes;     // output ring [kSlots][stage_bytes]
   float* s_red = reinterpret_cast<float*>(smem + 128 + kSlots * (p.slot_bytes + p.stage_bytes));
+  // dt=2 taps live in shared memory ([9][C2] float2, read back conflict-free) to keep the kernel
+  // at <= 128 registers, i.e. two 7-warp CTAs (4 warps per scheduler) resident per SM
+  const uint32_t w2_s = stage_s + kSlots * p.stage_bytes + 9 * CH * 4 /*s_red: Q<=9 rows*/;
 
   const int tid = threadIdx.x;
   const int slot = tid / C2, cp = tid - slot * C2;
@@ -107,16 +110,25 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     }
   }
 
-  float2 wr[27];
+  float2 wr[18];
   float2 bia = make_float2(0.f, 0.f);
   if (on) {
 #pragma unroll
-    for (int i = 0; i < 27; ++i) wr[i] = ld2(p.w + i * p.Cs + c);
+    for (int i = 0; i < 18; ++i) wr[i] = ld2(p.w + i * p.Cs + c);
     bia = ld2(p.bias + c);
   } else {
 #pragma unroll
-    for (int i = 0; i < 27; ++i) wr[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < 18; ++i) wr[i] = make_float2(0.f, 0.f);
   }
+  const uint32_t w2_t = w2_s + static_cast<uint32_t>(cp) * 8;
+  if (slot == 0) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float2 w = (c < p.Cs) ? ld2(p.w + (18 + i) * p.Cs + c) : make_float2(0.f, 0.f);
+      Pack<float>::sts2(w2_t + i * (C2 * 8), w);
+    }
+  }
+  __syncthreads();
 
   // Three accumulator sets rotate over output frames (set = frame % 3).  A set is (re)started by
   // the first tap of the dt=0 pass with the BN shift as addend; only frame 0 needs a preset.
@@ -162,20 +174,22 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     const uint32_t base = ring_s + s * p.slot_bytes + toff;
 #pragma unroll
     for (int dh = 0; dh < 3; ++dh) {
-      float2 v[BW];
+      float2 w2[3];
 #pragma unroll
-      for (int j = 0; j < BW; ++j) v[j] = Elem<T>::lds2(base + dh * RS + j * PS);
+      for (int dw = 0; dw < 3; ++dw) w2[dw] = Elem<float>::lds2(w2_t + (dh * 3 + dw) * (C2 * 8));
 #pragma unroll
-      for (int dw = 0; dw < 3; ++dw) {
-        const float2 w0 = wr[(0 * 3 + dh) * 3 + dw];
-        const float2 w1 = wr[(1 * 3 + dh) * 3 + dw];
-        const float2 w2 = wr[(2 * 3 + dh) * 3 + dw];
+      for (int jj = 0; jj < BW; ++jj) {
+        // one staged value feeds up to 3 output columns x 3 output frames, then dies
+        const float2 x = Elem<T>::lds2(base + dh * RS + jj * PS);
 #pragma unroll
-        for (int j = 0; j < SW; ++j) {
-          const float2 x = v[j * S + dw];
-          A0[j] = fma2(x, w0, (dh == 0 && dw == 0) ? bia : A0[j]);
-          A1[j] = fma2(x, w1, A1[j]);
-          A2[j] = fma2(x, w2, A2[j]);
+        for (int dw = 0; dw < 3; ++dw) {
+          const int jn = jj - dw;                       // = j * S for the output column j it feeds
+          if (jn >= 0 && jn % S == 0 && jn / S < SW) {  // resolved at compile time
+            const int j = jn / S;
+            A0[j] = fma2(x, wr[(0 * 3 + dh) * 3 + dw], (dh == 0 && dw == 0) ? bia : A0[j]);
+            A1[j] = fma2(x, wr[(1 * 3 + dh) * 3 + dw], A1[j]);
+            A2[j] = fma2(x, w2[dw], A2[j]);
+          }
         }
       }
     }
@@ -228,45 +242,45 @@ struct Plan {
   size_t smem;
 };
 
-static int pick_ch(int Cs) {
-  const int cand[3] = {72, 64, 56};
-  int best = 64, best_cost = 1 << 30;
-  for (int i = 0; i < 3; ++i) {
-    const int cost = (Cs + cand[i] - 1) / cand[i] * cand[i];
-    if (cost < best_cost) { best = cand[i]; best_cost = cost; }
+// Picks the channel chunk (56/64/72), strip width (7/8) and rows per tile (<= 224 threads, and at
+// most ~110 KB of shared memory so that two CTAs stay resident per SM) that minimise the padded
+// output volume (the kernel is FMA-bound), with the staged input volume as a secondary cost.
+static Plan make_plan(int H, int W, int Cs, int stride, int esize) {
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  const int chs[3] = {56, 64, 72}, sws[2] = {8, 7};
+  Plan best{};
+  double best_cost = 1e300;
+  for (int ci = 0; ci < 3; ++ci) {
+    for (int si = 0; si < 2; ++si) {
+      const int CH = chs[ci], SW = sws[si];
+      int qmax = 224 / (CH / 2);
+      if (qmax > 9) qmax = 9;
+      if (qmax > Ho) qmax = Ho;
+      for (int Q = qmax; Q >= 1; --Q) {
+        Plan pl;
+        pl.CH = CH; pl.SW = SW; pl.Q = Q;
+        pl.chunks = (Cs + CH - 1) / CH;
+        pl.BW = (SW - 1) * stride + 3;
+        pl.BH = (Q - 1) * stride + 3;
+        pl.box_bytes = pl.BH * pl.BW * CH * esize;
+        pl.slot_bytes = (pl.box_bytes + 127) / 128 * 128;
+        pl.stage_bytes = (Q * SW * CH * esize + 127) / 128 * 128;
+        pl.smem = 128 /*align*/ + 128 /*barriers*/ +
+                  (size_t)kSlots * (pl.slot_bytes + pl.stage_bytes) + (size_t)9 * CH * sizeof(float) /*s_red*/ +
+                  (size_t)9 * CH * sizeof(float) /*dt=2 taps*/;
+        if (pl.smem > 110 * 1024 && Q > 1) continue;
+        pl.threads = (Q * (CH / 2) + 31) / 32 * 32;
+        pl.tiles_w = (Wo + SW - 1) / SW;
+        pl.tiles_h = (Ho + Q - 1) / Q;
+        const double tiles = (double)pl.tiles_w * pl.tiles_h * pl.chunks;
+        const double work = tiles * Q * SW * CH;
+        const double staged = tiles * pl.BH * pl.BW * CH;
+        const double cost = work + 0.1 * staged + 1e-3 * tiles;
+        if (cost < best_cost) { best_cost = cost; best = pl; }
+      }
+    }
   }
   return best;
-}
-
-static Plan make_plan(int H, int W, int Cs, int stride, int esize) {
-  Plan pl;
-  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
-  pl.CH = pick_ch(Cs);
-  pl.chunks = (Cs + pl.CH - 1) / pl.CH;
-  const int c8 = (Wo + 7) / 8 * 8, c7 = (Wo + 6) / 7 * 7;
-  pl.SW = (c7 < c8) ? 7 : 8;
-  const int qmax = (288 / (pl.CH / 2)) < 9 ? (288 / (pl.CH / 2)) : 9;
-  int bestq = qmax, best_cost = 1 << 30;
-  for (int q = qmax; q >= 4; --q) {
-    const int cost = (Ho + q - 1) / q * q;
-    if (cost < best_cost) { bestq = q; best_cost = cost; }
-  }
-  if (Ho < bestq) bestq = Ho;
-  pl.BW = (pl.SW - 1) * stride + 3;
-  // keep two CTAs per SM resident: at most ~110 KB of shared memory per CTA
-  for (pl.Q = bestq;; --pl.Q) {
-    pl.BH = (pl.Q - 1) * stride + 3;
-    pl.box_bytes = pl.BH * pl.BW * pl.CH * esize;
-    pl.slot_bytes = (pl.box_bytes + 127) / 128 * 128;
-    pl.stage_bytes = (pl.Q * pl.SW * pl.CH * esize + 127) / 128 * 128;
-    pl.smem = 128 /*align*/ + 128 /*barriers*/ + (size_t)kSlots * (pl.slot_bytes + pl.stage_bytes) +
-              (size_t)pl.Q * pl.CH * sizeof(float);
-    if (pl.smem <= 110 * 1024 || pl.Q == 1) break;
-  }
-  pl.threads = (pl.Q * (pl.CH / 2) + 31) / 32 * 32;
-  pl.tiles_w = (Wo + pl.SW - 1) / pl.SW;
-  pl.tiles_h = (Ho + pl.Q - 1) / pl.Q;
-  return pl;
 }
 
 template <typename T, int S, int SW, int CH>
@@ -280,6 +294,8 @@ static int launch(const CUtensorMap& tm, const CUtensorMap& tmo, const Params& p
       set_error("x3d_dw3x3x3_fwd: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e));
       return X3D_ERR_LAUNCH;
     }
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     configured = pl.smem;
   }
   dim3 grid(pl.tiles_w * pl.tiles_h, pl.chunks, N);
@@ -303,9 +319,10 @@ static int dispatch(const CUtensorMap& tm, const CUtensorMap& tmo, const Params&
 
 using namespace x3d;
 
-extern "C" int x3d_dw_partial_blocks(int T, int H, int W, int C, int stride) {
+extern "C" int x3d_dw_partial_blocks(int T, int H, int W, int C, int stride, int dtype) {
   if (T <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 || (stride != 1 && stride != 2)) return 0;
-  const dwt::Plan pl = dwt::make_plan(H, W, C, stride, 2);
+  if (dtype != X3D_F32 && dtype != X3D_BF16) return 0;
+  const dwt::Plan pl = dwt::make_plan(H, W, C, stride, dtype == X3D_BF16 ? 2 : 4);
   return pl.tiles_w * pl.tiles_h;
 }
 

@@ -145,7 +145,7 @@ def dw_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: int, pa
     out = torch.empty((N, T, Ho, Wo, C), dtype=x.dtype, device=x.device)
     partial = None
     if want_se:
-        nblk = lib().x3d_dw_partial_blocks(T, H, W, C, stride)
+        nblk = lib().x3d_dw_partial_blocks(T, H, W, C, stride, _dt(x))
         if nblk <= 0:
             raise _lib.X3DLibError("x3d_dw_partial_blocks rejected the shape")
         partial = torch.empty((N, nblk, C), dtype=torch.float32, device=x.device)
