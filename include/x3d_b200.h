@@ -61,6 +61,13 @@ int x3d_stem_fwd(const void* in, int in_dtype, const float* ws, const float* wt,
                  const float* bias, void* out, int out_dtype,
                  int N, int T, int H, int W, int C, int kt, void* stream);
 
+/* Same operation on the tensor cores, bf16 output (the kernel the bf16 path uses): the two convs
+ * are merged into one kt x3x3 implicit GEMM (exact: nothing non-linear sits between them).
+ *   wc  bf16 [kt][4][32][8]: wc[dt][k/8][c][k%8] = ws[k][c] * wt[dt][c] (BN scale folded),
+ *       k = (dh*3+dw)*3+ci < 27, c < C; zero elsewhere.   C <= 32. */
+int x3d_stem_tc_fwd(const void* in, int in_dtype, const void* wc, const float* bias, void* out,
+                    int N, int T, int H, int W, int C, int kt, void* stream);
+
 /* ---- Pointwise (1x1x1) convolution as a GEMM, SIMT fp32-accumulate path ---------------------
  * One entry point for Bottleneck.a+bn_a+relu (model.py:306-308), Bottleneck.c+bn_c with the
  * SE-scale/swish prologue and the residual add + ReLU of ResBlock (model.py:311-318,389-392),

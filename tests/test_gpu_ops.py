@@ -49,6 +49,32 @@ def test_stem_mixed_dtypes():
     assert_close(to_np(got), want, torch.bfloat16, "stem f32->bf16")
 
 
+def _pack_stem_tc(ks, kt, C):
+    ws = ks.reshape(27, C).astype(np.float64)
+    wt = kt.reshape(5, C).astype(np.float64)
+    wc = np.zeros((5, 4, 32, 8), np.float64)
+    for k in range(27):
+        wc[:, k // 8, :C, k % 8] = ws[k][None, :] * wt
+    return to_dev(wc, torch.bfloat16)
+
+
+@pytest.mark.parametrize("in_dtype", DT)
+@pytest.mark.parametrize("N,T,H,W,C", [(2, 4, 32, 32, 24), (1, 5, 37, 45, 24), (1, 13, 18, 50, 32),
+                                       (2, 1, 8, 8, 24), (1, 16, 64, 64, 24), (1, 3, 91, 31, 24)])
+def test_stem_tcgen05(in_dtype, N, T, H, W, C):
+    rng = np.random.default_rng(N * 1000 + H + 1)
+    x = _q(rng.normal(size=(N, T, H, W, 3)), in_dtype)
+    ks = rng.normal(size=(1, 3, 3, 3, C)).astype(np.float32) * 0.3
+    kt = rng.normal(size=(5, 1, 1, 1, C)).astype(np.float32) * 0.5
+    bias = rng.normal(size=C).astype(np.float32) * 0.2
+    want = np.maximum(np_ops.stem_convs(x, ks, kt) + bias, 0.0)
+    got = _ops().stem_tc_fwd(to_dev(x, in_dtype), _pack_stem_tc(ks, kt, C), to_dev(bias))
+    torch.cuda.synchronize()
+    assert got.dtype == torch.bfloat16 and got.shape == want.shape
+    # operands are rounded to bf16 (clip values and merged weights): error ~ 2^-8 of the scale
+    assert rel_err(to_np(got), want) < 1.5e-2
+
+
 # ------------------------------------------------------------------------------- channelwise
 DW_CASES = [  # N, T, H, W, C, stride  -- covers both SAME-pad cases, odd extents, all strip widths
     (2, 4, 8, 8, 56, 1), (1, 16, 14, 14, 216, 1), (1, 13, 23, 23, 112, 1), (1, 4, 7, 7, 432, 1),

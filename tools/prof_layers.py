@@ -54,4 +54,6 @@ for si, (Hin, cin, inner, cout) in enumerate(stages):
                    (xb.numel() + 2 * M * K) * 2)
 if a.what in ("stem", "all"):
     x = rnd(N, T, a.size, a.size, 3); ws = rnd(27, 24, dtype=torch.float32); wt = rnd(5, 24, dtype=torch.float32); b = rnd(24, dtype=torch.float32)
-    timeit(f"stem {a.size}", lambda: ops.stem_fwd(x, ws, wt, b, torch.bfloat16), (x.numel() + N * T * S0 * S0 * 24) * 2)
+    timeit(f"stem simt {a.size}", lambda: ops.stem_fwd(x, ws, wt, b, torch.bfloat16), (x.numel() + N * T * S0 * S0 * 24) * 2)
+    wc = rnd(5, 4, 32, 8)
+    timeit(f"stem tcgen05 {a.size}", lambda: ops.stem_tc_fwd(x, wc, b), (x.numel() + N * T * S0 * S0 * 24) * 2)

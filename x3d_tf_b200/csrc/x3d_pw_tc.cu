@@ -8,8 +8,9 @@
 //     swizzle, out-of-bounds rows/channels zero-filled, so K and M need no padding in HBM);
 //   * one elected thread issues tcgen05.mma (M=128, N=NT, K=16) into a double-buffered TMEM
 //     accumulator, tcgen05.commit releases ring stages / publishes the accumulator via mbarriers;
-//   * 4 epilogue warps read TMEM with tcgen05.ld, add bias (+ residual), ReLU, pack bf16, store;
-//   * optional prologue (projection conv of SE blocks, model.py:311-317): 4 transform warps apply
+//   * 2 groups of 4 epilogue warps (one per TMEM accumulator) read TMEM with tcgen05.ld, add bias
+//     (+ residual, prefetched), ReLU, pack bf16 into swizzled staging and TMA-store full lines;
+//   * optional prologue (projection conv, model.py:311-317): 8 transform warps apply
 //     swish(se[clip,k] * a) in place on each landed stage before the MMA consumes it.
 //
 // Reference call sites replaced: Bottleneck.a/bn_a/relu (model.py:306-308), Bottleneck.c/bn_c +
@@ -87,12 +88,13 @@ struct Params {
   int relu, swish;
 };
 
-constexpr int kThreadsPlain = 192, kThreadsPro = 320;
+constexpr int kEpiWarps = 8, kProWarps = 8, kOutBufs = 4;   // 2 epilogue groups x 2 staging buffers
+constexpr int kThreadsPlain = 64 + 32 * kEpiWarps, kThreadsPro = kThreadsPlain + 32 * kProWarps;
 
 template <bool kPro>
 __global__ void __launch_bounds__(kPro ? kThreadsPro : kThreadsPlain, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-             const Params p) {
+             const __grid_constant__ CUtensorMap tmD, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -102,7 +104,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   uint8_t* sW = smem;
   uint8_t* sA = sW + p.KC * w_chunk_bytes;
-  float* sBias = reinterpret_cast<float*>(sA + p.stages * kStageBytes);
+  uint8_t* sD = sA + p.stages * kStageBytes;          // [kOutBufs] 128x64 bf16 output staging, 128B swizzle
+  float* sBias = reinterpret_cast<float*>(sD + kOutBufs * kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);
   uint64_t* full = bars;                      // [stages]  TMA landed
   uint64_t* empty = full + p.stages;          // [stages]  MMA done reading
@@ -119,15 +122,16 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
+    prefetch_tmap(&tmD);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
-      mbar_init(&xform[s], 128);
+      mbar_init(&xform[s], 32 * kProWarps);
     }
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
-      mbar_init(&t_empty[i], 128);
+      mbar_init(&t_empty[i], 16 * kEpiWarps);          // one epilogue group (4 warps) per buffer
     }
     fence_barrier_init();
   }
@@ -193,103 +197,152 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp < 6) {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+  } else if (warp < 2 + kEpiWarps) {
+    // ------------------------------------------------------------------ epilogue (2 groups x 4 warps)
+    // Group g owns TMEM accumulator g and every second tile, so two epilogues are in flight; inside
+    // a group warp w reads TMEM lane quarter w%4.  Results are staged in 128B-swizzled shared
+    // memory and leave as full lines through TMA box stores (clipped at M / Nc).
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    long it = 0;
-    for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int as = static_cast<int>(it & 1);
-      const uint32_t aph = static_cast<uint32_t>((it >> 1) & 1);
-      mbar_wait(&t_full[as], aph);
-      tcgen05_after_sync();
-      const long row = tile * kBlockM + q * 32 + lane;
+    const int grp = (warp - 2) >> 2;
+    const bool leader = q == 2 && lane == 0;      // first warp of each group is warp 2 / warp 6
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+    const int r_loc = q * 32 + lane;              // row inside the tile
+    const uint32_t sw_row = static_cast<uint32_t>(r_loc) * 128, sw_x = static_cast<uint32_t>(r_loc & 7);
+    const int n_sub = (p.NT + 63) >> 6;
+    const uint32_t stage0 = smem_u32(sD + grp * 2 * kStageBytes);
+    const uint32_t bias_s = smem_u32(sBias);
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                           static_cast<uint32_t>(grp * p.NT);
+    uint32_t sub_ctr = 0, aph = 0;
+    for (long tile = blockIdx.x + static_cast<long>(grp) * gridDim.x; tile < num_tiles;
+         tile += 2L * gridDim.x, aph ^= 1) {
+      const long row = tile * kBlockM + r_loc;
       const bool row_ok = row < p.M;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                             static_cast<uint32_t>(as * p.NT);
-      bf16* drow = p.D + row * p.ldd + n0;
-      const bf16* rrow = p.R ? p.R + row * p.ldr + n0 : nullptr;
-      for (int c0 = 0; c0 < p.NT; c0 += 16) {
-        if (n0 + c0 >= p.Nc) break;               // uniform across the CTA
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
+      const bf16* rrow = (p.R && row_ok) ? p.R + row * p.ldr + n0 : nullptr;
+      // residual of the first sub-tile is requested before the accumulator is waited for
+      uint4 rr[8];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int cc = c0 + h * 8;
-          if (n0 + cc >= p.Nc || !row_ok) continue;
-          float y[8];
+      for (int c = 0; c < 8; ++c)
+        rr[c] = (rrow && c * 8 < p.NT && n0 + c * 8 < p.Nc) ? __ldg(reinterpret_cast<const uint4*>(rrow + c * 8))
+                                                           : make_uint4(0, 0, 0, 0);
+      mbar_wait(&t_full[grp], aph);
+      tcgen05_after_sync();
+      for (int sb = 0; sb < n_sub; ++sb, ++sub_ctr) {
+        if (n0 + sb * 64 >= p.Nc) break;          // uniform across the CTA
+        const uint32_t buf = stage0 + (sub_ctr & 1) * kStageBytes + sw_row;
+        if (sb > 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[h * 8 + j]) + sBias[cc + j];
-          if (rrow) {
-            float r[8];
-            ld8(rrow + cc, r);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] += r[j];
+          for (int c = 0; c < 8; ++c) {
+            const int cc = sb * 64 + c * 8;
+            rr[c] = (rrow && cc < p.NT && n0 + cc < p.Nc) ? __ldg(reinterpret_cast<const uint4*>(rrow + cc))
+                                                         : make_uint4(0, 0, 0, 0);
           }
-          if (p.relu) {
+        }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+        for (int g = 0; g < 4; ++g) {
+          const int c0 = sb * 64 + g * 16;        // column inside the N tile
+          if (c0 >= p.NT || n0 + c0 >= p.Nc) continue;
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cc = c0 + h * 8;
+            float4 b0, b1;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(bias_s + cc * 4));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(bias_s + cc * 4 + 16));
+            float2 y[4];
+            y[0] = __fadd2_rn(make_float2(__uint_as_float(v[h * 8 + 0]), __uint_as_float(v[h * 8 + 1])), make_float2(b0.x, b0.y));
+            y[1] = __fadd2_rn(make_float2(__uint_as_float(v[h * 8 + 2]), __uint_as_float(v[h * 8 + 3])), make_float2(b0.z, b0.w));
+            y[2] = __fadd2_rn(make_float2(__uint_as_float(v[h * 8 + 4]), __uint_as_float(v[h * 8 + 5])), make_float2(b1.x, b1.y));
+            y[3] = __fadd2_rn(make_float2(__uint_as_float(v[h * 8 + 6]), __uint_as_float(v[h * 8 + 7])), make_float2(b1.z, b1.w));
+            if (p.R) {
+              const uint4 ru = rr[g * 2 + h];
+              const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                y[j] = __fadd2_rn(y[j], make_float2(__uint_as_float(rw[j] << 16),
+                                                    __uint_as_float(rw[j] & 0xffff0000u)));
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 t = __float22bfloat162_rn(y[j]);
+              if (p.relu) t = __hmax2(t, zero2);
+              o[j] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            const uint32_t chunk = static_cast<uint32_t>(g * 2 + h);          // 16-byte chunk 0..7
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + ((chunk ^ sw_x) << 4)),
+                         "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
           }
-          uint4 o;
-          __nv_bfloat162 t0 = __floats2bfloat162_rn(y[0], y[1]);
-          __nv_bfloat162 t1 = __floats2bfloat162_rn(y[2], y[3]);
-          __nv_bfloat162 t2 = __floats2bfloat162_rn(y[4], y[5]);
-          __nv_bfloat162 t3 = __floats2bfloat162_rn(y[6], y[7]);
-          o.x = *reinterpret_cast<uint32_t*>(&t0);
-          o.y = *reinterpret_cast<uint32_t*>(&t1);
-          o.z = *reinterpret_cast<uint32_t*>(&t2);
-          o.w = *reinterpret_cast<uint32_t*>(&t3);
-          *reinterpret_cast<uint4*>(drow + cc) = o;
+        }
+        if (sb == n_sub - 1 || n0 + (sb + 1) * 64 >= p.Nc) {
+          tcgen05_before_sync();                  // last TMEM read of this tile is done
+          mbar_arrive(&t_empty[grp]);
+        }
+        fence_proxy_async();
+        // the store issued after the previous barrier has (long since) finished reading its
+        // staging buffer: checked here, off the critical path, so that buffer is free again for
+        // everybody once this barrier is passed
+        if (leader) tma_store_wait_read<0>();
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (leader) {
+          tma_store_2d(&tmD, stage0 + (sub_ctr & 1) * kStageBytes, n0 + sb * 64,
+                       static_cast<int>(tile * kBlockM));
+          tma_store_commit();
         }
       }
-      tcgen05_before_sync();
-      mbar_arrive(&t_empty[as]);
     }
+    if (leader) tma_store_wait_read<0>();
   } else if (kPro) {
-    // ------------------------------------------------------------------ prologue transform (warps 6..9)
-    const int tt = threadIdx.x - 192;             // 0..127
+    // ------------------------------------------------------------------ prologue transform (8 warps)
+    const int tt = threadIdx.x - kThreadsPlain;   // 0..255
     const int pchunk = tt & 7;                    // physical 16-byte chunk inside the 128-byte row
+    const uint32_t rpc = static_cast<uint32_t>(p.rows_per_clip > 0 ? p.rows_per_clip : 0x7fffffff);
     int s = 0;
     uint32_t ph = 0;
     for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const uint32_t row0 = static_cast<uint32_t>(tile * kBlockM);
+      const uint32_t clip0 = row0 / rpc, rem0 = row0 - clip0 * rpc;
       for (int kc = 0; kc < p.KC; ++kc) {
         mbar_wait(&full[s], ph);
-        uint8_t* st = sA + s * kStageBytes;
-#pragma unroll 2
-        for (int r0 = 0; r0 < kBlockM; r0 += 16) {
+        const uint32_t st = smem_u32(sA + s * kStageBytes);
+#pragma unroll
+        for (int r0 = 0; r0 < kBlockM; r0 += 32) {
           const int r = r0 + (tt >> 3);
-          const long row = tile * kBlockM + r;
           const int k = kc * kBlockK + ((pchunk ^ (r & 7)) << 3);
-          if (row < p.M && k < p.Kc) {
-            uint4* ptr = reinterpret_cast<uint4*>(st + r * 128 + pchunk * 16);
-            uint4 u = *ptr;
-            uint32_t w[4] = {u.x, u.y, u.z, u.w};
-            float sc[8];
+          if (row0 + r < static_cast<uint32_t>(p.M) && k < p.Kc) {
+            const uint32_t addr = st + r * 128 + pchunk * 16;
+            uint32_t w[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+            float2 sc[4];
             if (p.se) {
-              const float* sp = p.se + (row / p.rows_per_clip) * p.Kc + k;
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(sp) + 1);
-              sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w;
-              sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+              uint32_t x = rem0 + r, clip = clip0;
+              while (x >= rpc) { x -= rpc; ++clip; }
+              const float4* sp = reinterpret_cast<const float4*>(p.se + static_cast<long>(clip) * p.Kc + k);
+              const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+              sc[0] = make_float2(s0.x, s0.y); sc[1] = make_float2(s0.z, s0.w);
+              sc[2] = make_float2(s1.x, s1.y); sc[3] = make_float2(s1.z, s1.w);
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) sc[j] = 1.f;
+              for (int j = 0; j < 4; ++j) sc[j] = make_float2(1.f, 1.f);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float a = __uint_as_float(w[j] << 16) * sc[2 * j];
-              float b = __uint_as_float(w[j] & 0xffff0000u) * sc[2 * j + 1];
+              float2 a = __fmul2_rn(make_float2(__uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u)), sc[j]);
               if (p.swish) {
-                float ta, tb;
-                asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(0.5f * a));
-                asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(0.5f * b));
-                a = a * fmaf(0.5f, ta, 0.5f);
-                b = b * fmaf(0.5f, tb, 0.5f);
+                const float2 hx = __fmul2_rn(a, make_float2(0.5f, 0.5f));
+                float2 t;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(hx.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(hx.y));
+                a = __fmul2_rn(a, __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f)));
               }
-              __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-              w[j] = *reinterpret_cast<uint32_t*>(&t);
+              __nv_bfloat162 t2 = __float22bfloat162_rn(a);
+              w[j] = *reinterpret_cast<uint32_t*>(&t2);
             }
-            *ptr = make_uint4(w[0], w[1], w[2], w[3]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
           }
         }
         fence_proxy_async();
@@ -347,19 +400,22 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   const int KC = (k16_total + 3) / 4;                 // chunks that actually hold data
   const int k16_last = k16_total - (KC - 1) * 4;
   (void)kc_n;
-  const int budget = device_max_smem() - 1024 /*align*/ - 1024 /*bias*/ - 512 /*barriers*/;
+  const int budget = device_max_smem() - 1024 /*align*/ - 1024 /*bias*/ - 512 /*barriers*/ -
+                     tc::kOutBufs * tc::kStageBytes /*output staging*/;
+  // The epilogue stores 64-column boxes, so with more than one N tile the tile width must be a
+  // multiple of 64 (a box of one tile must never reach into its neighbour's columns).
   int n_tiles = (a->Npad + 255) / 256;
   int NT = 0, stages = 0;
   for (;; ++n_tiles) {
-    NT = (((a->Npad + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+    const int per = (a->Npad + n_tiles - 1) / n_tiles;
+    NT = n_tiles == 1 ? (per + 15) / 16 * 16 : (per + 63) / 64 * 64;
     const int wbytes = KC * NT * 128;
     stages = (budget - wbytes) / tc::kStageBytes;
-    if (stages >= 3 || NT <= 16) break;
+    if (stages >= 3 || NT <= 64) break;
   }
   X3D_REQUIRE(stages >= 2, X3D_ERR_UNSUPPORTED, "x3d_pw_tc_fwd: K=%d too large for shared memory", a->K);
   if (stages > 8) stages = 8;
-  X3D_REQUIRE((long)n_tiles * NT <= a->Npad + 15 || n_tiles * NT <= ((a->Npad + 15) / 16) * 16 + 16 * n_tiles,
-              X3D_ERR_UNSUPPORTED, "x3d_pw_tc_fwd: tiling error");
+  n_tiles = (a->Nc + NT - 1) / NT;                     // tiles that hold real columns
   int tmem_cols = 32;
   while (tmem_cols < 2 * NT) tmem_cols *= 2;
   X3D_REQUIRE(tmem_cols <= 512, X3D_ERR_UNSUPPORTED, "x3d_pw_tc_fwd: NT=%d needs too much TMEM", NT);
@@ -372,13 +428,16 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   X3D_REQUIRE(tc::make_map_2d(&tmW, a->Wp, (uint64_t)a->Kpad, (uint64_t)a->Npad, (uint64_t)a->Kpad * 2, 64, (uint32_t)NT),
               X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: tensor map for W failed (Kpad=%d Npad=%d NT=%d)", a->Kpad, a->Npad, NT);
 
+  CUtensorMap tmD;
+  X3D_REQUIRE(tc::make_map_2d(&tmD, a->D, (uint64_t)a->Nc, (uint64_t)a->M, (uint64_t)a->ldd * 2, 64, 128),
+              X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: tensor map for D failed (Nc=%d M=%ld ldd=%d)", a->Nc, (long)a->M, a->ldd);
   tc::Params p;
   p.bias = a->bias; p.R = static_cast<const bf16*>(a->R); p.se = a->se; p.D = static_cast<bf16*>(a->D);
   p.M = a->M; p.rows_per_clip = a->rows_per_clip; p.Kc = a->K; p.Nc = a->Nc; p.ldr = a->ldr; p.ldd = a->ldd;
   p.NT = NT; p.KC = KC; p.k16_last = k16_last; p.stages = stages; p.tmem_cols = tmem_cols;
   p.relu = a->relu; p.swish = a->swish;
 
-  const size_t smem = 1024 + (size_t)KC * NT * 128 + (size_t)stages * tc::kStageBytes + 1024 + 512;
+  const size_t smem = 1024 + (size_t)KC * NT * 128 + (size_t)(stages + tc::kOutBufs) * tc::kStageBytes + 1024 + 512;
   const long num_tiles = (a->M + tc::kBlockM - 1) / tc::kBlockM;
   int gx = device_sm_count() / n_tiles;
   if (gx < 1) gx = 1;
@@ -390,11 +449,11 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   if (pro) {
     e = cudaFuncSetAttribute(tc::pw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
-    tc::pw_tc_kernel<true><<<grid, tc::kThreadsPro, smem, st>>>(tmA, tmW, p);
+    tc::pw_tc_kernel<true><<<grid, tc::kThreadsPro, smem, st>>>(tmA, tmW, tmD, p);
   } else {
     e = cudaFuncSetAttribute(tc::pw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
-    tc::pw_tc_kernel<false><<<grid, tc::kThreadsPlain, smem, st>>>(tmA, tmW, p);
+    tc::pw_tc_kernel<false><<<grid, tc::kThreadsPlain, smem, st>>>(tmA, tmW, tmD, p);
   }
   return check_launch("x3d_pw_tc_fwd");
 }

@@ -226,6 +226,7 @@ class PointwiseConv:
 # only choose between equivalent CUDA kernels).
 class Options:
     pointwise = "tc"          # "tc": tcgen05 kernel for bf16 activations; "simt": CUDA-core GEMM
+    stem = "tc"               # "tc": tcgen05 implicit-GEMM stem for bf16 activations; "simt"
 
 
 def _use_tc() -> bool:
@@ -253,14 +254,25 @@ class X3D_Stem(Layer):
             s, t = self._fold_bn("bn", self.bn_eps)
             ws = self._vars["conv_s/kernel"].reshape(27, C).astype(np.float64)
             wt = self._vars["conv_t/kernel"].reshape(self.temp_filter_size, C).astype(np.float64) * s
-            self._dev[key] = {"ws": _dev_f32(_pad_to(ws, 1, cs), device),
-                              "wt": _dev_f32(_pad_to(wt, 1, cs), device),
-                              "bias": _dev_f32(_pad_to(t, 0, cs), device)}
+            d = {"ws": _dev_f32(_pad_to(ws, 1, cs), device),
+                 "wt": _dev_f32(_pad_to(wt, 1, cs), device),
+                 "bias": _dev_f32(_pad_to(t, 0, cs), device)}
+            if cs <= 32 and self.temp_filter_size == 5:
+                # merged kt x3x3 kernel for the tensor-core stem: [dt][k/8][c][k%8], K and C padded to 32
+                wc = np.zeros((self.temp_filter_size, 4, 32, 8), np.float64)
+                full = ws[None, :, :] * wt[:, None, :]                    # [dt, 27, C]
+                for k in range(27):
+                    wc[:, k // 8, :C, k % 8] = full[:, k, :]
+                d["wc"] = torch.from_numpy(wc.astype(np.float32)).to(device).to(
+                    torch.bfloat16).contiguous()
+            self._dev[key] = d
         return self._dev[key]
 
     def _forward(self, x: torch.Tensor, out_dtype) -> torch.Tensor:
         d = self._prep(x.device)
         ops.Profiler.tag = "stem"
+        if out_dtype == torch.bfloat16 and "wc" in d and Options.stem == "tc":
+            return ops.stem_tc_fwd(x, d["wc"], d["bias"])
         return ops.stem_fwd(x, d["ws"], d["wt"], d["bias"], out_dtype)
 
     def call(self, input, training: bool = False):

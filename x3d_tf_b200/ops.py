@@ -90,6 +90,21 @@ def stem_fwd(x: torch.Tensor, ws: torch.Tensor, wt: torch.Tensor, bias: torch.Te
     return out
 
 
+def stem_tc_fwd(x: torch.Tensor, wc: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """Tensor-core stem: fp32 or bf16 clips in, bf16 activations out."""
+    _req(x, "x")
+    N, T, H, W, ci = x.shape
+    if ci != 3:
+        raise ValueError("stem input must have 3 channels")
+    C = bias.numel()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty((N, T, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+    _launch("x3d_stem_tc_fwd", lambda: lib().x3d_stem_tc_fwd(
+        x.data_ptr(), _dt(x), wc.data_ptr(), bias.data_ptr(), out.data_ptr(), N, T, H, W, C,
+        wc.shape[0], _stream()))
+    return out
+
+
 def pw_fwd(a: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, M: int, K: int,
            Nc: int, out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
            residual: Optional[torch.Tensor] = None, se: Optional[torch.Tensor] = None,
