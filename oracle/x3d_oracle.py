@@ -10,13 +10,19 @@ layer semantics below restate TF's published behaviour (Conv3D `valid`/`same`, g
 BatchNormalization inference, GlobalAveragePooling3D, Dense, Softmax) at the reference's own
 call sites, each cited as `model.py:line`.
 
-PARITY UNPINNED: the reference ships no tests and no numeric golden vectors for this path
-(SURVEY.md section 8c), and neither TF nor the checkpoint data shards are present, so no
-output of the real Keras model can be generated here.  What IS pinned (tests/test_oracle_*):
-the structural golden data the reference ships (per-stage output shapes and parameter counts
-in `models/*/X3D_*.txt`, every variable name/shape of `models/*/model.index`), and a second,
-independent numpy implementation (`oracle/np_ops.py`) of the two layers whose TF semantics are
-not the torch default (SAME-padded strided channelwise conv; the padded stem).
+PARITY PARTIALLY PINNED.  The reference ships no tests and no numeric golden vectors for this
+path; TensorFlow and the checkpoint data shards are absent, so no output
+of the real Keras/TensorFlow stack can be generated here.  What IS pinned:
+  * `tests/golden/ref_*.npz`: outputs of the reference's OWN, unmodified `model.py` executed in the
+    build container on `oracle/tf_shim` (numpy float64 Keras primitives), for all five variants --
+    everything `model.py`/`utils.py`/`configs/default.py` decide (graph, rounding, SE placement by
+    the global block counter, call order, view averaging, variable names) is the reference's code;
+    this oracle matches those logits to 1e-10 (`tests/test_reference_golden.py`);
+  * the structural golden data the reference ships (per-stage shapes and parameter counts in
+    `models/*/X3D_*.txt`, every variable name/shape of `models/*/model.index`);
+  * a second, independent numpy implementation (`oracle/np_ops.py`) of the two layers whose TF
+    semantics are not the torch default (SAME-padded strided channelwise conv; the padded stem).
+Still unpinned: the numerics of TensorFlow's own kernels, restated from documented TF semantics.
 
 Weights are a dict {checkpoint attribute path -> numpy float32 array}, layouts as TF stores
 them (conv kernels DHWIO, dense [in,out]); names per SURVEY.md Appendix C.

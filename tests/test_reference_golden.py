@@ -1,0 +1,102 @@
+"""Fixtures produced by the reference's own model.py (run on oracle/tf_shim in the build
+container by tests/golden/make_reference_golden.py) pin (a) the CPU oracle and (b) the CUDA
+path.  Nothing here reads /root/reference."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import x3d_oracle as O
+from x3d_tf_b200.arch import build_arch, variable_shapes
+from x3d_tf_b200.config import get_config
+from x3d_tf_b200.synth import synthetic_weights
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(glob.glob(os.path.join(GOLDEN, "ref_*.npz")))
+
+
+def _load(path):
+    z = np.load(path)
+    meta = json.loads(str(z["meta"]))
+    cfg = get_config(meta["variant"], freeze=False)
+    cfg.TEST.NUM_TEMPORAL_VIEWS, cfg.TEST.NUM_SPATIAL_CROPS = meta["views"], meta["crops"]
+    cfg.freeze()
+    return z, meta, cfg
+
+
+def test_fixtures_present():
+    assert len(CASES) >= 5
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[4:-4] for p in CASES])
+def test_variable_names_and_se_placement_match_reference_code(path):
+    z, meta, cfg = _load(path)
+    arch = build_arch(cfg)
+    mine = variable_shapes(arch)
+    ref = {str(k): tuple(json.loads(str(s))) for k, s in zip(z["var_names"], z["var_shapes"])}
+    assert {k: tuple(v) for k, v in mine.items()} == ref
+    se_ref = sorted(str(k) for k in z["se_blocks"])
+    se_mine = sorted(f"stages/{b.stage}/stage/layer_with_weights-{b.index}/bottleneck/se_fc1/kernel"
+                     for b in arch.blocks if b.has_se)
+    assert se_mine == se_ref
+
+
+def test_x3d_m_reference_names_equal_shipped_checkpoint_index(checkpoint_index):
+    """Names the reference's code produces (via the shim's object-graph walk) == the model
+    variables listed in the shipped models/X3D-M/model.index."""
+    z, _, _ = _load(os.path.join(GOLDEN, "ref_m_1view.npz"))
+    suffix = "/.ATTRIBUTES/VARIABLE_VALUE"
+    names = set()
+    for entry in checkpoint_index["keys"]:          # [key, dtype, shape, offset, size]
+        k = entry[0]
+        if k.endswith(suffix) and ".OPTIMIZER_SLOT" not in k and not k.startswith("optimizer/"):
+            names.add(k[:-len(suffix)])
+    assert len(names) == 476
+    assert names == {str(k) for k in z["var_names"]}
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[4:-4] for p in CASES])
+def test_oracle_matches_reference_model_py(path):
+    z, meta, cfg = _load(path)
+    W = synthetic_weights(build_arch(cfg), seed=meta["weight_seed"])
+    taps = {}
+    got = O.forward(W, O.OracleSpec.from_cfg(cfg), z["clips"], torch.float64, taps=taps)
+    np.testing.assert_allclose(got["logits"], z["logits"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(got["probs"], z["probs"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(O.to_ndhwc(taps["conv1"]), z["conv1"], rtol=0, atol=1e-5)
+    arch = build_arch(cfg)
+    for s in range(4):
+        last = max(b.index for b in arch.blocks if b.stage == s)
+        np.testing.assert_allclose(O.to_ndhwc(taps[f"stages/{s}/stage/layer_with_weights-{last}"]),
+                                   z[f"stage{s}"], rtol=0, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [("float32", 1e-4), ("bfloat16", 2e-2)])
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[4:-4] for p in CASES])
+def test_cuda_path_matches_reference_model_py(path, dtype, tol):
+    """north_star tolerance: fp32 logits within 1e-4 relative, bf16 within 2e-2 relative with
+    identical top-1 (relative = max |err| / max |logit|)."""
+    from x3d_tf_b200 import model as M
+    z, meta, cfg = _load(path)
+    W = synthetic_weights(build_arch(cfg), seed=meta["weight_seed"])
+    M.reset_block_counters()
+    m = M.X3D(cfg, dtype=dtype, use_cuda_graph=False)
+    m.set_weights_dict(W)
+    probs = m(torch.from_numpy(z["clips"]).cuda())
+    torch.cuda.synchronize()
+    logits = m.last_logits.float().cpu().numpy()
+    err = np.abs(logits - z["logits"]).max() / np.abs(z["logits"]).max()
+    assert err < tol, err
+    p = probs.float().cpu().numpy()
+    assert p.shape == z["probs"].shape
+    assert np.abs(p - z["probs"]).max() < (1e-5 if dtype == "float32" else 2e-3)
+    if True:
+        # identical top-1 wherever the reference's own margin exceeds the error bound
+        ref_sorted = np.sort(z["logits"], axis=1)
+        margin = ref_sorted[:, -1] - ref_sorted[:, -2]
+        safe = margin > 2 * tol * np.abs(z["logits"]).max()
+        assert (logits.argmax(1)[safe] == z["logits"].argmax(1)[safe]).all()
