@@ -121,6 +121,19 @@ int x3d_avgpool_fwd(const void* in, float* out, int N, int64_t P, int C, int dty
 int x3d_softmax_viewmean_fwd(const float* logits, float* probs, int N, int ncls, int num_preds,
                              void* stream);
 
+/* ---- Row gather of the strided shortcut conv: ResBlock.residual, model.py:360-367 ------------
+ * The 1x1x1 'valid' conv with stride (1,s,s) reads input pixels (t, ho*s, wo*s) only.  This
+ * copies them into a dense matrix  out[(nt*Ho+ho)*Wo+wo, 0:C] = in[nt, ho*s, wo*s, 0:C]
+ * (Ho=(Hi-1)/s+1, Wo=(Wi-1)/s+1, NT = N*T) that x3d_pw_tc_fwd then multiplies by the kernel. */
+int x3d_gather_rows_fwd(const void* in, void* out, int NT, int Hi, int Wi, int stride, int C,
+                        int dtype, void* stream);
+
+/* ---- Head fully-connected layers: fc1 (+ReLU) and fc2 (+bias), model.py:119-121 -------------
+ * (dropout, model.py:120, is the identity at inference.)  Small-M fp32 GEMM that streams the
+ * weights once:  D[M, Nc] = act(A[M, K] . Wt[K, Nc] + bias),  act = ReLU if relu. */
+int x3d_head_fc_fwd(const float* A, const float* Wt, const float* bias, float* D, int M, int K,
+                    int Nc, int lda, int ldw, int ldd, int relu, void* stream);
+
 /* ---- Pointwise convolution on the 5th-gen tensor cores (bf16 in, fp32 accumulate in TMEM) ----
  * Same contract as x3d_pw_fwd for a_dtype = d_dtype = X3D_BF16 and gather == 0, but the weights
  * are pre-packed bf16: Wp [Npad, Kpad] (K contiguous), Npad % 16 == 0, Kpad % 64 == 0, zero

@@ -159,3 +159,27 @@ def test_checkpoint_round_trip(tmp_path):
     status.expect_partial().assert_existing_objects_matched()
     m2(x)
     assert torch.equal(l1, m2.last_logits)
+
+
+def test_predict_pipelined_host_batches_equal_call():
+    """X3D.predict (pinned host batches, H2D on a copy stream overlapped with the previous
+    forward, two graph slots sharing one memory pool) returns exactly what X3D.call returns."""
+    m, cfg, W, spec = _model("X3D_XS", dtype="bfloat16", views=2, graph=True)
+    batches = [torch.from_numpy(synthetic_clips(4, 4, 64, 64, cfg.DATA.MEAN, cfg.DATA.STD, seed=s))
+               .to(torch.bfloat16).pin_memory() for s in range(5)]
+    want = [m(b).float().cpu().clone() for b in batches]
+    got = list(m.predict(iter(batches)))
+    assert len(got) == 5
+    for g, w in zip(got, want):
+        assert g.shape == (2, 400) and torch.equal(g, w)
+    # a second pass reuses the captured slots; numpy float32 input and a different shape also work
+    got2 = list(m.predict(b.float().numpy() for b in batches[:3]))
+    for g, w in zip(got2, want):
+        assert torch.allclose(g, w, atol=2e-3)
+    odd = synthetic_clips(2, 4, 46, 38, cfg.DATA.MEAN, cfg.DATA.STD, seed=9)
+    (p,) = list(m.predict([odd]))
+    ref = O.forward(W, spec, odd, torch.float64)["probs"]
+    assert np.abs(p.numpy() - ref).max() < 2e-3
+    assert list(m.predict([])) == []
+    with pytest.raises(ValueError):
+        list(m.predict([odd[:1]]))

@@ -265,3 +265,45 @@ def test_error_reporting():
         _ops().dw_fwd(x, torch.zeros((27, 12), device=dev()), torch.zeros(12, device=dev()), 1, 1, 1, False)
     with pytest.raises(ValueError):
         _ops().avgpool_fwd(torch.zeros((1, 2, 2, 2, 8)))       # CPU tensor: no CPU path
+
+
+# ------------------------------------------------------------------------------- gather / head
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("H,W,stride,C", [(8, 8, 2, 24), (7, 9, 2, 48), (23, 23, 2, 96), (5, 6, 1, 24),
+                                          (91, 91, 2, 24)])
+def test_gather_rows_is_bit_exact(dtype, H, W, stride, C):
+    """Index work: the sampled rows must be copied bit for bit (model.py:360-367, 'valid',
+    stride (1,s,s) => positions 0, s, 2s, ...)."""
+    rng = np.random.default_rng(H * W + C)
+    x = to_dev(rng.normal(size=(2, 3, H, W, C)), dtype)
+    got = _ops().gather_rows_fwd(x, stride)
+    want = x[:, :, ::stride, ::stride, :].contiguous().view(-1, C)
+    assert got.shape == want.shape
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("M,K,N,relu", [(80, 432, 2048, True), (80, 2048, 400, False), (1, 432, 2048, True),
+                                        (7, 64, 20, False), (130, 72, 36, True)])
+def test_head_fc(M, K, N, relu):
+    rng = np.random.default_rng(M + K + N)
+    a = rng.normal(size=(M, K)).astype(np.float32)
+    w = (rng.normal(size=(K, N)) / np.sqrt(K)).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    want = a.astype(np.float64) @ w.astype(np.float64) + b
+    if relu:
+        want = np.maximum(want, 0)
+    got = _ops().head_fc_fwd(to_dev(a), to_dev(w), to_dev(b), K=K, Nc=N, relu=relu)
+    assert_close(to_np(got), want, torch.float32, "head fc")
+
+
+def test_shortcut_tc_path_matches_oracle():
+    """ResBlock shortcut (residual + bn_r, model.py:386-388) through gather + tcgen05 GEMM."""
+    rng = np.random.default_rng(5)
+    N, T, H, W, K, Nc = 2, 3, 23, 17, 24, 48
+    x = bf16_round(rng.normal(size=(N, T, H, W, K)))
+    k = rng.normal(size=(1, 1, 1, K, Nc)).astype(np.float32) / 5
+    bias = rng.normal(size=Nc).astype(np.float32)
+    want = np_ops.pointwise_conv_valid(x, bf16_round(k), 2) + bias
+    rows = _ops().gather_rows_fwd(to_dev(x, torch.bfloat16), 2)
+    got = _ops().pw_tc_fwd(rows, _pack_tc(k.reshape(K, Nc)), to_dev(bias), M=rows.shape[0], K=K, Nc=Nc)
+    assert_close(to_np(got).reshape(want.shape), want, torch.bfloat16, "shortcut tc")

@@ -26,6 +26,46 @@ __global__ void fma_kernel(float* out, int iters, float a0) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// FFMA2 with the operand pattern of the channelwise stencil: acc[set][col] += x[jj] * w[set][dw].
+// MODE 0: 9 consecutive FFMA2 share x (operand reuse possible); MODE 1: x, w and acc all change
+// from one FFMA2 to the next (3 distinct register pairs per instruction, no reuse).
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) stencil_fma_kernel(const float2* __restrict__ src, float* out, int iters) {
+  float2 x[10], w[9], acc[3][8];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) x[i] = src[threadIdx.x + 32 * i];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) w[i] = src[threadIdx.x + 32 * (10 + i)];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[a][j] = make_float2(a, j);
+  for (int it = 0; it < iters; ++it) {
+    if (MODE == 0) {
+#pragma unroll
+      for (int jj = 0; jj < 10; ++jj)
+#pragma unroll
+        for (int dw = 0; dw < 3; ++dw) {
+          const int j = jj - dw;
+          if (j >= 0 && j < 8) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) acc[a][j] = __ffma2_rn(x[jj], w[a * 3 + dw], acc[a][j]);
+          }
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 72; ++i)
+        acc[i % 3][(i / 3) % 8] = __ffma2_rn(x[i % 10], w[i % 9], acc[i % 3][(i / 3) % 8]);
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += acc[a][j].x + acc[a][j].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void copy_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -55,6 +95,22 @@ int main() {
       if (rep) printf("%-24s %8.3f ms  %8.2f TFMA/s  (%.1f FMA/clk/SM at %d MHz nominal)\n", names[mode], ms,
                       fmas / ms / 1e9, fmas / (ms * 1e-3) / p.multiProcessorCount / (p.clockRate * 1e3), p.clockRate / 1000);
     }
+  }
+  {
+    float2* src; cudaMalloc(&src, 32 * 32 * sizeof(float2)); cudaMemset(src, 0, 32 * 32 * sizeof(float2));
+    const char* nm[2] = {"FFMA2 stencil pattern (x shared by 9)", "FFMA2 3 distinct operands, no reuse"};
+    for (int mode = 0; mode < 2; ++mode)
+      for (int rep = 0; rep < 2; ++rep) {
+        const int it2 = 4000, bl = p.multiProcessorCount * 2, th = 256;
+        cudaEventRecord(e0);
+        if (mode == 0) stencil_fma_kernel<0><<<bl, th>>>(src, out, it2);
+        else stencil_fma_kernel<1><<<bl, th>>>(src, out, it2);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double fmas = (double)bl * th * it2 * 72 * 2;
+        if (rep) printf("%-40s %8.3f ms  %8.2f TFMA/s  (%.1f FMA/clk/SM at %d MHz nominal)\n", nm[mode], ms,
+                        fmas / ms / 1e9, fmas / (ms * 1e-3) / p.multiProcessorCount / (p.clockRate * 1e3), p.clockRate / 1000);
+      }
   }
   size_t n = (size_t)1 << 26;   // 1 GiB in uint4
   uint4 *a, *b; cudaMalloc(&a, n * 16); cudaMalloc(&b, n * 16); cudaMemset(a, 1, n * 16);

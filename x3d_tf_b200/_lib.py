@@ -61,6 +61,10 @@ SIGNATURES = {
     "x3d_softmax_viewmean_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p]),
     "x3d_pw_tc_fwd": (C.c_int, [C.POINTER(PwTcArgs), C.c_void_p]),
+    "x3d_gather_rows_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_void_p]),
+    "x3d_head_fc_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 
 _lock = threading.Lock()

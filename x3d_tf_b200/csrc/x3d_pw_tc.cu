@@ -297,41 +297,58 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (leader) tma_store_wait_read<0>();
   } else if (kPro) {
     // ------------------------------------------------------------------ prologue transform (8 warps)
+    // In place on the landed stage: a <- swish(se[clip, k] * a).  A thread owns one physical
+    // 16-byte chunk column (8 channels) of rows tt/8 + 32*i; because 32 is a multiple of the
+    // swizzle period its channel offset k is the same for all 4 rows, so the 8 SE factors are
+    // fetched once per stage (tiles that straddle two clips take the per-row path).  The 4 shared
+    // loads are issued back to back before any math so their latency overlaps.
     const int tt = threadIdx.x - kThreadsPlain;   // 0..255
     const int pchunk = tt & 7;                    // physical 16-byte chunk inside the 128-byte row
+    const int rbase = tt >> 3;                    // 0..31
+    const int kin = (pchunk ^ (rbase & 7)) << 3;  // channel offset inside the 64-wide chunk
     const uint32_t rpc = static_cast<uint32_t>(p.rows_per_clip > 0 ? p.rows_per_clip : 0x7fffffff);
     int s = 0;
     uint32_t ph = 0;
     for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const uint32_t row0 = static_cast<uint32_t>(tile * kBlockM);
       const uint32_t clip0 = row0 / rpc, rem0 = row0 - clip0 * rpc;
+      const bool one_clip = rem0 + kBlockM <= rpc;            // whole tile inside one clip
       for (int kc = 0; kc < p.KC; ++kc) {
+        const int k = kc * kBlockK + kin;
+        const bool k_ok = k < p.Kc;                           // beyond Kc the stage holds TMA zeros
+        float2 sc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sc[j] = make_float2(1.f, 1.f);
+        if (p.se && k_ok && one_clip) {
+          const float4* sp = reinterpret_cast<const float4*>(p.se + static_cast<long>(clip0) * p.Kc + k);
+          const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+          sc[0] = make_float2(s0.x, s0.y); sc[1] = make_float2(s0.z, s0.w);
+          sc[2] = make_float2(s1.x, s1.y); sc[3] = make_float2(s1.z, s1.w);
+        }
         mbar_wait(&full[s], ph);
-        const uint32_t st = smem_u32(sA + s * kStageBytes);
+        if (k_ok) {
+          const uint32_t addr0 = smem_u32(sA + s * kStageBytes) + rbase * 128 + pchunk * 16;
+          uint32_t w[4][4];
 #pragma unroll
-        for (int r0 = 0; r0 < kBlockM; r0 += 32) {
-          const int r = r0 + (tt >> 3);
-          const int k = kc * kBlockK + ((pchunk ^ (r & 7)) << 3);
-          if (row0 + r < static_cast<uint32_t>(p.M) && k < p.Kc) {
-            const uint32_t addr = st + r * 128 + pchunk * 16;
-            uint32_t w[4];
+          for (int i = 0; i < 4; ++i)
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
-            float2 sc[4];
-            if (p.se) {
-              uint32_t x = rem0 + r, clip = clip0;
-              while (x >= rpc) { x -= rpc; ++clip; }
-              const float4* sp = reinterpret_cast<const float4*>(p.se + static_cast<long>(clip) * p.Kc + k);
-              const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
-              sc[0] = make_float2(s0.x, s0.y); sc[1] = make_float2(s0.z, s0.w);
-              sc[2] = make_float2(s1.x, s1.y); sc[3] = make_float2(s1.z, s1.w);
-            } else {
+                         : "=r"(w[i][0]), "=r"(w[i][1]), "=r"(w[i][2]), "=r"(w[i][3])
+                         : "r"(addr0 + i * (32 * 128)));
 #pragma unroll
-              for (int j = 0; j < 4; ++j) sc[j] = make_float2(1.f, 1.f);
+          for (int i = 0; i < 4; ++i) {
+            if (p.se && !one_clip) {
+              uint32_t x = rem0 + rbase + 32 * i, clip = clip0;
+              while (x >= rpc) { x -= rpc; ++clip; }
+              if (static_cast<long>(clip) * rpc + x < p.M) {
+                const float4* sp = reinterpret_cast<const float4*>(p.se + static_cast<long>(clip) * p.Kc + k);
+                const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+                sc[0] = make_float2(s0.x, s0.y); sc[1] = make_float2(s0.z, s0.w);
+                sc[2] = make_float2(s1.x, s1.y); sc[3] = make_float2(s1.z, s1.w);
+              }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float2 a = __fmul2_rn(make_float2(__uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u)), sc[j]);
+              float2 a = __fmul2_rn(make_float2(__uint_as_float(w[i][j] << 16), __uint_as_float(w[i][j] & 0xffff0000u)), sc[j]);
               if (p.swish) {
                 const float2 hx = __fmul2_rn(a, make_float2(0.5f, 0.5f));
                 float2 t;
@@ -340,9 +357,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 a = __fmul2_rn(a, __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f)));
               }
               __nv_bfloat162 t2 = __float22bfloat162_rn(a);
-              w[j] = *reinterpret_cast<uint32_t*>(&t2);
+              w[i][j] = *reinterpret_cast<uint32_t*>(&t2);
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr0 + i * (32 * 128)), "r"(w[i][0]), "r"(w[i][1]), "r"(w[i][2]), "r"(w[i][3]) : "memory");
           }
         }
         fence_proxy_async();

@@ -322,6 +322,86 @@ pw_gemm_kernel(const PwParams p) {
   }
 }
 
+// =====================================================================================
+// Row gather for the strided shortcut conv (ResBlock.residual: 1x1x1, stride (1,s,s), 'valid',
+// model.py:360-367): copies the sampled pixels (n, t, ho*s, wo*s) into a dense [M_out, C] matrix
+// so that the tensor-core GEMM can consume them through a plain 2-D TMA map.  16-byte vectors,
+// grid-stride; reads 1/s^2 of the input rows, each exactly once.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long rows_out, int Ho,
+                   int Wo, int Hi, int Wi, int stride, int vec_per_row) {
+  const long total = rows_out * vec_per_row;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    long m = i / vec_per_row;
+    const int v = (int)(i - m * vec_per_row);
+    const int wo = (int)(m % Wo); m /= Wo;
+    const int ho = (int)(m % Ho); m /= Ho;            // m = n*T + t
+    const long src = (m * Hi + (long)ho * stride) * Wi + (long)wo * stride;
+    out[i] = __ldg(in + src * vec_per_row + v);
+  }
+}
+
+// =====================================================================================
+// Skinny GEMM for the head (fc1 + ReLU, fc2 + bias; model.py:119-121): M = clips (tens), so the
+// work is streaming the fp32 weights once.  CTA = 16 output columns x up to 128 rows; K is walked
+// in chunks of 64 staged in shared memory; thread = (column, row group of 8).
+constexpr int kSkN = 16, kSkK = 64, kSkRows = 8, kSkM = 16 * kSkRows;
+
+__global__ void __launch_bounds__(256)
+skinny_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
+                   const float* __restrict__ bias, float* __restrict__ D, int M, int K, int Nc,
+                   int lda, int ldw, int ldd, int relu) {
+  __shared__ __align__(16) float As[kSkM][kSkK + 4];
+  __shared__ __align__(16) float Ws[kSkK][kSkN];
+  const int tid = threadIdx.x, c = tid & 15, g = tid >> 4;
+  const int n0 = blockIdx.x * kSkN, m0 = blockIdx.y * kSkM;
+  const int rows = min(kSkM, M - m0);
+  float acc[kSkRows];
+#pragma unroll
+  for (int i = 0; i < kSkRows; ++i) acc[i] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += kSkK) {
+    __syncthreads();
+    for (int i = tid; i < kSkM * (kSkK / 4); i += 256) {
+      const int r = i / (kSkK / 4), kv = (i - r * (kSkK / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows && k0 + kv < K) v = __ldg(reinterpret_cast<const float4*>(A + (long)(m0 + r) * lda + k0 + kv));
+      *reinterpret_cast<float4*>(&As[r][kv]) = v;
+    }
+    for (int i = tid; i < kSkK * (kSkN / 4); i += 256) {
+      const int k = i / (kSkN / 4), nv = (i - k * (kSkN / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < K && n0 + nv < Nc) v = __ldg(reinterpret_cast<const float4*>(Wt + (long)(k0 + k) * ldw + n0 + nv));
+      *reinterpret_cast<float4*>(&Ws[k][nv]) = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < kSkK; k += 4) {
+      const float w0 = Ws[k][c], w1 = Ws[k + 1][c], w2 = Ws[k + 2][c], w3 = Ws[k + 3][c];
+#pragma unroll
+      for (int i = 0; i < kSkRows; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[g + 16 * i][k]);
+        acc[i] = fmaf(a.x, w0, acc[i]);
+        acc[i] = fmaf(a.y, w1, acc[i]);
+        acc[i] = fmaf(a.z, w2, acc[i]);
+        acc[i] = fmaf(a.w, w3, acc[i]);
+      }
+    }
+  }
+  const int col = n0 + c;
+  if (col >= Nc) return;
+  const float b = bias ? __ldg(bias + col) : 0.f;
+#pragma unroll
+  for (int i = 0; i < kSkRows; ++i) {
+    const int r = g + 16 * i;
+    if (r < rows) {
+      float y = acc[i] + b;
+      if (relu) y = fmaxf(y, 0.f);
+      D[(long)(m0 + r) * ldd + col] = y;
+    }
+  }
+}
+
 // --------------------------------------------------------------------------- host side
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -411,6 +491,36 @@ int x3d_pw_fwd(const x3d_pw_args* a, void* stream) {
   else
     X3D_REQUIRE(false, X3D_ERR_INVALID_ARG, "x3d_pw_fwd: unsupported dtype pair %d/%d", a->a_dtype, a->d_dtype);
   return check_launch("x3d_pw_fwd");
+}
+
+int x3d_gather_rows_fwd(const void* in, void* out, int NT, int Hi, int Wi, int stride, int C,
+                        int dtype, void* stream) {
+  X3D_REQUIRE(in && out, X3D_ERR_INVALID_ARG, "x3d_gather_rows_fwd: null pointer");
+  X3D_REQUIRE(NT > 0 && Hi > 0 && Wi > 0 && stride >= 1 && C > 0, X3D_ERR_INVALID_ARG, "x3d_gather_rows_fwd: bad extent");
+  X3D_REQUIRE(dtype == X3D_F32 || dtype == X3D_BF16, X3D_ERR_INVALID_ARG, "x3d_gather_rows_fwd: dtype %d", dtype);
+  const int es = dtype == X3D_BF16 ? 2 : 4;
+  X3D_REQUIRE((C * es) % 16 == 0, X3D_ERR_INVALID_ARG, "x3d_gather_rows_fwd: row of %d bytes is not a multiple of 16", C * es);
+  X3D_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, X3D_ERR_INVALID_ARG, "x3d_gather_rows_fwd: pointers must be 16-byte aligned");
+  const int Ho = (Hi - 1) / stride + 1, Wo = (Wi - 1) / stride + 1;
+  const long rows = (long)NT * Ho * Wo;
+  const int vpr = C * es / 16;
+  long blocks = (rows * vpr + 255) / 256;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  gather_rows_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out),
+                                                             rows, Ho, Wo, Hi, Wi, stride, vpr);
+  return check_launch("x3d_gather_rows_fwd");
+}
+
+int x3d_head_fc_fwd(const float* A, const float* Wt, const float* bias, float* D, int M, int K,
+                    int Nc, int lda, int ldw, int ldd, int relu, void* stream) {
+  X3D_REQUIRE(A && Wt && D, X3D_ERR_INVALID_ARG, "x3d_head_fc_fwd: null pointer");
+  X3D_REQUIRE(M > 0 && K > 0 && Nc > 0, X3D_ERR_INVALID_ARG, "x3d_head_fc_fwd: empty problem");
+  X3D_REQUIRE(K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && Nc % 4 == 0, X3D_ERR_INVALID_ARG, "x3d_head_fc_fwd: K/lda/ldw/Nc must be multiples of 4");
+  X3D_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Wt)) & 15) == 0, X3D_ERR_INVALID_ARG, "x3d_head_fc_fwd: pointers must be 16-byte aligned");
+  dim3 grid((Nc + kSkN - 1) / kSkN, (M + kSkM - 1) / kSkM);
+  X3D_REQUIRE(grid.y <= 65535, X3D_ERR_UNSUPPORTED, "x3d_head_fc_fwd: M too large");
+  skinny_gemm_kernel<<<grid, 256, 0, S(stream)>>>(A, Wt, bias, D, M, K, Nc, lda, ldw, ldd, relu);
+  return check_launch("x3d_head_fc_fwd");
 }
 
 }  // extern "C"

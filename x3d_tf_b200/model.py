@@ -434,7 +434,12 @@ class ResBlock(Layer):
             s = self.stride
             Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
             ops.Profiler.tag = "shortcut"
-            res = d["r"].run(x, N * T * Ho * Wo, use_tc=False, gather=(T, Ho, Wo, H, W, s))
+            if _use_tc() and x.dtype == torch.bfloat16:
+                # sampled pixels -> dense matrix -> tensor-core GEMM (bn_r folded)
+                rows = x.view(-1, x.shape[-1]) if s == 1 else ops.gather_rows_fwd(x, s)
+                res = d["r"].run(rows, N * T * Ho * Wo, use_tc=True)
+            else:
+                res = d["r"].run(x, N * T * Ho * Wo, use_tc=False, gather=(T, Ho, Wo, H, W, s))
         else:
             res = x
         return self.bottleneck._forward(x, residual=res, relu=True)
@@ -588,40 +593,55 @@ class X3D(Layer):
         for st in self.stages:
             out = st._forward(out)
         out = self.conv5._forward(out)
-        ops.Profiler.tag = "head"
+        ops.Profiler.tag = "head_pool"
         pooled = ops.avgpool_fwd(out)                                   # [N, C5s] fp32
         N = pooled.shape[0]
+        ops.Profiler.tag = "head_fc"
         f1 = self.fc1._prep(x.device)
-        h = ops.pw_fwd(pooled, f1.wt, None, M=N, K=f1.Ks, Nc=f1.Ns, relu=True)
+        h = ops.head_fc_fwd(pooled, f1.wt, None, K=f1.Ks, Nc=f1.Ns, relu=True)
         f2 = self.fc2._prep(x.device)
-        logits_p = ops.pw_fwd(h, f2.wt, f2.bias, M=N, K=f2.Ks, Nc=f2.Ns)
+        logits_p = ops.head_fc_fwd(h, f2.wt, f2.bias, K=f2.Ks, Nc=f2.Ns)
         logits = logits_p if f2.Ns == self.num_classes else \
             logits_p[:, :self.num_classes].contiguous()
+        ops.Profiler.tag = "head_softmax"
         probs = ops.softmax_viewmean_fwd(logits, 1 if training else self._num_preds)
         return probs, logits
+
+    def _check_input(self, shape):
+        if len(shape) != 5 or shape[-1] != self.cfg.DATA.NUM_INPUT_CHANNELS:
+            raise ValueError(f"expected NDHWC clips with {self.cfg.DATA.NUM_INPUT_CHANNELS} channels, "
+                             f"got shape {tuple(shape)}")
+        if shape[0] % self._num_preds != 0:
+            raise ValueError(f"batch {shape[0]} must be a multiple of "
+                             f"NUM_TEMPORAL_VIEWS*NUM_SPATIAL_CROPS = {self._num_preds}")
+
+    def _graph(self, shape, dtype, device, slot: int = 0, training: bool = False):
+        """(graph, static input, static probs, static logits) for one input shape.  Captured on
+        first use (after one eager run that warms lazy CUDA state).  Slots > 0 are extra captures
+        over their own input/output buffers that share slot 0's memory pool (replays are
+        stream-ordered), used by `predict` to overlap the H2D copy of the next batch."""
+        key = (tuple(shape), dtype, str(device), Options.pointwise, Options.stem, slot)
+        if key not in self._graphs:
+            static_in = torch.zeros(tuple(shape), dtype=dtype, device=device)
+            self._forward(static_in, training)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            pool = None
+            if slot:
+                pool = self._graph(shape, dtype, device, 0, training)[0].pool()
+            with torch.cuda.graph(g, pool=pool):
+                s_probs, s_logits = self._forward(static_in, training)
+            self._graphs[key] = (g, static_in, s_probs, s_logits)
+        return self._graphs[key]
 
     def call(self, input, training: bool = False):
         self._no_training(training)
         x = _as_device_clip(input, self._device)
-        if x.shape[-1] != self.cfg.DATA.NUM_INPUT_CHANNELS:
-            raise ValueError(f"expected {self.cfg.DATA.NUM_INPUT_CHANNELS} input channels")
-        if x.shape[0] % self._num_preds != 0:
-            raise ValueError(f"batch {x.shape[0]} must be a multiple of "
-                             f"NUM_TEMPORAL_VIEWS*NUM_SPATIAL_CROPS = {self._num_preds}")
+        self._check_input(x.shape)
         if not self._use_graph:
             probs, self.last_logits = self._forward(x, training)
             return probs
-        key = (tuple(x.shape), x.dtype, str(x.device), Options.pointwise)
-        if key not in self._graphs:
-            # first call with this shape: eager run (also warms lazy CUDA state), then capture
-            probs, logits = self._forward(x, training)
-            torch.cuda.current_stream().synchronize()
-            static_in = x.clone()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                s_probs, s_logits = self._forward(static_in, training)
-            self._graphs[key] = (g, static_in, s_probs, s_logits)
-        g, static_in, s_probs, s_logits = self._graphs[key]
+        g, static_in, s_probs, s_logits = self._graph(x.shape, x.dtype, x.device, 0, training)
         if x.data_ptr() != static_in.data_ptr():
             static_in.copy_(x, non_blocking=True)
         g.replay()
@@ -631,10 +651,68 @@ class X3D(Layer):
     def static_input(self, shape, dtype=torch.bfloat16):
         """The captured graph's input buffer for `shape` (fill it in place and pass it to
         `call` to skip the staging copy).  None until the first call with that shape."""
-        for (shp, dt, _, _), (_, static_in, _, _) in self._graphs.items():
-            if tuple(shp) == tuple(shape) and dt == dtype:
+        for key, (_, static_in, _, _) in self._graphs.items():
+            if tuple(key[0]) == tuple(shape) and key[1] == dtype and key[-1] == 0:
                 return static_in
         return None
+
+    def predict(self, batches, training: bool = False):
+        """Generator over host batches -> host probabilities: what `model.predict(dataset)` /
+        `model.evaluate(dataset)` do in the reference (eval.py:83-89, Keras prefetches the next
+        batch while the current one runs).  Each batch is an NDHWC numpy array or CPU tensor
+        (pinned memory makes the copy asynchronous); its host->device copy is issued on a copy
+        stream while the previous batch computes, the forward is one CUDA-graph replay, and the
+        probabilities come back through a pinned buffer.  Yields float32 CPU tensors
+        [videos, classes] in order."""
+        self._no_training(training)
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device: the X3D path has no CPU implementation")
+        device = self._device or torch.device("cuda", torch.cuda.current_device())
+        main = torch.cuda.current_stream(device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device)
+        cs = self._copy_stream
+        slots: Dict[tuple, dict] = {}
+
+        def stage(hb, slot):
+            if isinstance(hb, np.ndarray):
+                hb = torch.from_numpy(np.ascontiguousarray(hb))
+            if hb.dtype in (torch.float16, torch.float64):
+                hb = hb.to(torch.float32)
+            self._check_input(hb.shape)
+            g, static_in, s_probs, s_logits = self._graph(hb.shape, hb.dtype, device, slot, training)
+            st = slots.setdefault((tuple(hb.shape), hb.dtype, slot), {
+                "host_out": torch.empty(tuple(s_probs.shape), dtype=torch.float32).pin_memory(),
+                "done": torch.cuda.Event(), "copied": torch.cuda.Event()})
+            st.update(g=g, s_probs=s_probs, s_logits=s_logits)
+            cs.wait_event(st["done"])               # the replay that last read this buffer is over
+            cs.wait_stream(main) if not st.get("used") else None
+            st["used"] = True
+            with torch.cuda.stream(cs):
+                static_in.copy_(hb, non_blocking=True)
+                st["copied"].record(cs)
+            return st
+
+        it = iter(batches)
+        first = next(it, None)
+        if first is None:
+            return
+        nxt, pending, i = stage(first, 0), None, 0
+        while nxt is not None:
+            cur = nxt
+            hb = next(it, None)
+            nxt = stage(hb, (i + 1) & 1) if hb is not None else None
+            main.wait_event(cur["copied"])
+            cur["g"].replay()
+            cur["host_out"].copy_(cur["s_probs"], non_blocking=True)
+            cur["done"].record(main)
+            self.last_logits = cur["s_logits"]
+            if pending is not None:
+                pending["done"].synchronize()
+                yield pending["host_out"].clone()
+            pending, i = cur, i + 1
+        pending["done"].synchronize()
+        yield pending["host_out"].clone()
 
     def summary(self, input_shape) -> str:
         """Keras-style table (`model.py:129-132`, dumps in `models/*/X3D_*.txt`)."""

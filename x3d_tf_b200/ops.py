@@ -152,6 +152,31 @@ def pw_tc_fwd(a: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], *
     return out
 
 
+def gather_rows_fwd(x: torch.Tensor, stride: int) -> torch.Tensor:
+    """[N,T,H,W,C] -> dense [N*T*Ho*Wo, C] of the pixels a stride-(1,s,s) 'valid' 1x1x1 conv reads."""
+    _req(x, "x")
+    N, T, H, W, C = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty((N * T * Ho * Wo, C), dtype=x.dtype, device=x.device)
+    _launch("x3d_gather_rows_fwd", lambda: lib().x3d_gather_rows_fwd(
+        x.data_ptr(), out.data_ptr(), N * T, H, W, stride, C, _dt(x), _stream()))
+    return out
+
+
+def head_fc_fwd(a: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, K: int, Nc: int,
+                relu: bool = False) -> torch.Tensor:
+    """Small-M fp32 GEMM of the head: act(a[M,K] @ wt[K,Nc] + bias)."""
+    _req(a, "a")
+    if a.dtype != torch.float32:
+        raise TypeError("head_fc_fwd needs float32 input")
+    M = a.shape[0]
+    out = torch.empty((M, Nc), dtype=torch.float32, device=a.device)
+    _launch("x3d_head_fc_fwd", lambda: lib().x3d_head_fc_fwd(
+        a.data_ptr(), wt.data_ptr(), _ptr(bias), out.data_ptr(), M, K, Nc, a.shape[1], wt.shape[1],
+        Nc, int(relu), _stream()))
+    return out
+
+
 def dw_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: int, pad_h: int,
            pad_w: int, want_se: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     _req(x, "x")
