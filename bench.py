@@ -54,7 +54,7 @@ def algorithmic_work(arch, T, H, W, esize):
     plan = plan_shapes(arch, T, H, W)
     c1 = arch.stem_channels
     out = {k: {"bytes": 0.0, "macs": 0.0} for k in
-           ("stem", "a", "b", "c", "shortcut", "conv5", "head")}
+           ("stem", "a", "b", "ab", "c", "shortcut", "conv5", "head")}
     out["stem"]["bytes"] = (plan.input.P * 3 + plan.stem.P * c1) * esize
     out["stem"]["macs"] = plan.stem.P * c1 * (27 + arch.temp_filter)
     level = plan.stem
@@ -65,6 +65,9 @@ def algorithmic_work(arch, T, H, W, esize):
         out["a"]["macs"] += b.cin * b.cinner * p_in
         out["b"]["bytes"] += b.cinner * (p_in + p_out) * esize
         out["b"]["macs"] += 27 * b.cinner * p_out
+        # fused expand+channelwise launch: only the block input and the channelwise output touch HBM
+        out["ab"]["bytes"] += (b.cin * p_in + b.cinner * p_out) * esize
+        out["ab"]["macs"] += b.cin * b.cinner * p_in + 27 * b.cinner * p_out
         out["c"]["bytes"] += (b.cinner + 2 * b.cout) * p_out * esize      # in + residual + out
         out["c"]["macs"] += b.cinner * b.cout * p_out
         if b.has_shortcut:
@@ -303,19 +306,32 @@ def run_b200(args):
             c["hbm_frac"] = c["GBps"] / hbm
             c["tflops"] = 2 * work[tag]["macs"] * clips / (c["ms"] * 1e-3) / 1e12
         c["ms"] = round(c["ms"], 4)
-    b = classes.get("b", {"ms": float("nan"), "launches": 0})
-    b_bytes = work["b"]["bytes"] * clips
+    fused = "ab" in classes and "b" not in classes
+    if fused:
+        b = classes["ab"]
+        b_bytes = work["ab"]["bytes"] * clips
+        kname = "ab_fused_kernel (expand 1x1x1 + BN + ReLU -> channelwise 3x3x3 + BN + SE sums)"
+    else:
+        b = classes.get("b", {"ms": float("nan"), "launches": 0})
+        b_bytes = work["b"]["bytes"] * clips
+        kname = "dw_tma_kernel (channelwise 3x3x3 + BN + SE sums)"
     achieved = b_bytes / (b["ms"] * 1e-3) / 1e9
-    roofline = {"kernel": "dw3x3x3_kernel (channelwise 3x3x3 + BN + SE sums)", "bound": "hbm",
+    roofline = {"kernel": kname, "bound": "hbm",
                 "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                 "traffic": None, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
                 "launches_per_step": b["launches"],
                 "algorithmic_bytes_per_step": b_bytes,
                 "avg_launch_ms": b["ms"] / max(b["launches"], 1),
                 "how": "CUDA events around each launch of one eager pass over the timed batch"}
-    total_bytes = sum(w["bytes"] for w in work.values()) * clips
+    if fused:
+        # the stencil half runs on the fp32 FMA pipe: 27 MAC per output against the packed-FFMA2
+        # rate measured for this operand pattern (profiles/r01_microbench_fma_copy.txt)
+        roofline["stencil_fma_tmacs"] = work["b"]["macs"] * clips / (b["ms"] * 1e-3) / 1e12
+        roofline["stencil_fma_frac_of_31.4_TFMA/s"] = roofline["stencil_fma_tmacs"] / 31.4
+        roofline["unfused_equivalent_GBps"] = (work["a"]["bytes"] + work["b"]["bytes"]) * clips / (b["ms"] * 1e-3) / 1e9
+    total_bytes = sum(w["bytes"] for k, w in work.items() if k != "ab") * clips
     pw_macs = (work["a"]["macs"] + work["c"]["macs"]) * clips
-    pw_ms = classes.get("a", {"ms": 0})["ms"] + classes.get("c", {"ms": 0})["ms"]
+    pw_ms = classes.get("a", classes.get("ab", {"ms": 0}))["ms"] + classes.get("c", {"ms": 0})["ms"]
     extra = {"whole_model_hbm_frac_layerwise": total_bytes / (ms_max / args.steps * 1e-3) / 1e9 / hbm,
              "pointwise_tensor_pipe_util": (2 * pw_macs / (pw_ms * 1e-3) / 1e12 / tflops) if pw_ms else None,
              "kernel_classes": classes}

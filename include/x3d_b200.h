@@ -147,6 +147,23 @@ typedef struct x3d_pw_tc_args {
 } x3d_pw_tc_args;
 int x3d_pw_tc_fwd(const x3d_pw_tc_args* args, void* stream);
 
+/* ---- Fused expand + channelwise: Bottleneck.a + bn_a + ReLU + b + bn_b (+ se_pool sums), ----
+ * ---- model.py:306-312, as one kernel (bf16 storage) ------------------------------------------
+ * Same result as x3d_pw_tc_fwd(relu=1) followed by x3d_dw3x3x3_fwd, but the `inner`-wide tensor
+ * between the two convolutions stays in shared memory / TMEM (it is rounded to bf16 there exactly
+ * as the unfused path rounds it when it stores it).
+ *   x    [N,T,H,W,Cin] bf16          block input, Cin = stored channels (multiple of 8)
+ *   wa   bf16 [Npad, Kpad]           packed expand kernel as for x3d_pw_tc_fwd (BN scale folded)
+ *   bias_a [C] fp32                  bn_a shift;   wb [27,C] fp32, bias_b [C] fp32 as for x3d_dw3x3x3_fwd
+ *   out  [N,T,Ho,Wo,C] bf16          Ho=ceil(H/s), Wo=ceil(W/s);  C = stored inner channels
+ *   se_partial [N, nblk, C] fp32 or NULL, nblk = x3d_expand_dw_partial_blocks(...)
+ * Returns X3D_ERR_UNSUPPORTED when no tile plan fits (the caller then runs the two kernels). */
+int x3d_expand_dw_partial_blocks(int T, int H, int W, int Cin, int C, int stride);
+int x3d_expand_dw_fwd(const void* x, const void* wa, const float* bias_a, const float* wb,
+                      const float* bias_b, void* out, float* se_partial, int N, int T, int H,
+                      int W, int Cin, int C, int Kpad, int Npad, int stride, int pad_h, int pad_w,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,6 +105,48 @@ def test_channelwise(dtype, N, T, H, W, C, stride):
     assert p2 is None and torch.equal(out, out2)
 
 
+# ------------------------------------------------------------------------------- fused expand + channelwise
+AB_CASES = [  # N, T, H, W, Cin, C, stride  -- every stage shape class, odd extents, both pads, K > 64
+    (2, 4, 16, 16, 24, 56, 1), (1, 16, 14, 14, 96, 216, 1), (1, 13, 23, 23, 48, 112, 1),
+    (1, 4, 8, 8, 192, 432, 1), (1, 5, 12, 9, 24, 56, 1), (1, 4, 32, 32, 24, 56, 2),
+    (1, 13, 23, 23, 24, 112, 2), (1, 4, 46, 46, 24, 56, 2), (2, 3, 18, 26, 96, 432, 2),
+    (1, 1, 16, 16, 48, 216, 1), (1, 2, 9, 20, 136, 632, 1), (1, 16, 28, 28, 48, 112, 1),
+    (1, 3, 20, 20, 72, 168, 2)]
+
+
+@pytest.mark.parametrize("N,T,H,W,Cin,C,stride", AB_CASES)
+def test_fused_expand_channelwise_tcgen05(N, T, H, W, Cin, C, stride):
+    """x3d_expand_dw_fwd == bf16(relu(x.Wa + ta)) -> channelwise conv, the unfused pair's result."""
+    from x3d_tf_b200.arch import same_pad
+    ops = _ops()
+    if ops.expand_dw_supported(T, H, W, Cin, C, stride) <= 0:
+        pytest.skip("no fused tile plan for this shape (the model falls back to the two kernels)")
+    rng = np.random.default_rng(H * 100 + W + C + stride + Cin)
+    x = bf16_round(rng.normal(size=(N, T, H, W, Cin)))
+    wa = bf16_round(rng.normal(size=(Cin, C)) / np.sqrt(Cin))
+    ta = rng.normal(size=C).astype(np.float32) * 0.3
+    k = rng.normal(size=(3, 3, 3, 1, C)).astype(np.float32) * 0.3
+    tb = rng.normal(size=C).astype(np.float32) * 0.2
+    a = np.maximum(x.reshape(-1, Cin).astype(np.float64) @ wa.astype(np.float64) + ta, 0.0)
+    a = bf16_round(a).reshape(N, T, H, W, C)                     # the ring holds bf16, like HBM would
+    want = np_ops.channelwise_conv_same(a, k, stride) + tb
+    npad, kpad = (C + 15) // 16 * 16, (Cin + 63) // 64 * 64
+    wp = np.zeros((npad, kpad), np.float32)
+    wp[:C, :Cin] = wa.T
+    _, ph, _ = same_pad(H, 3, stride)
+    _, pw, _ = same_pad(W, 3, stride)
+    out, partial = ops.expand_dw_fwd(to_dev(x, torch.bfloat16), to_dev(wp, torch.bfloat16), to_dev(ta),
+                                     to_dev(k.reshape(27, C)), to_dev(tb), stride, ph, pw, True)
+    torch.cuda.synchronize()
+    assert_close(to_np(out), want, torch.bfloat16, "fused expand+channelwise")
+    sums = to_np(partial).astype(np.float64).sum(1)
+    np.testing.assert_allclose(sums, want.sum((1, 2, 3)), rtol=2e-4,
+                               atol=2e-4 * np.abs(want).sum((1, 2, 3)).max())
+    out2, p2 = ops.expand_dw_fwd(to_dev(x, torch.bfloat16), to_dev(wp, torch.bfloat16), to_dev(ta),
+                                 to_dev(k.reshape(27, C)), to_dev(tb), stride, ph, pw, False)
+    assert p2 is None and torch.equal(out, out2)
+
+
 # ------------------------------------------------------------------------------- pointwise
 def _pw_ref(a, w, bias, res=None, se=None, rpc=0, swish=False, relu=False):
     a = np.asarray(a, np.float64)

@@ -227,6 +227,7 @@ class PointwiseConv:
 class Options:
     pointwise = "tc"          # "tc": tcgen05 kernel for bf16 activations; "simt": CUDA-core GEMM
     stem = "tc"               # "tc": tcgen05 implicit-GEMM stem for bf16 activations; "simt"
+    fuse_expand = True        # bf16 + "tc": run a/bn_a/relu/b/bn_b as ONE kernel (x3d_expand_dw_fwd)
 
 
 def _use_tc() -> bool:
@@ -369,13 +370,19 @@ class Bottleneck(Layer):
         N, T, H, W, _ = x.shape
         ci = _pad8(self.inner)
         tc = _use_tc()
-        ops.Profiler.tag = "a"
-        a = d["a"].run(x, N * T * H * W, use_tc=tc, relu=True).view(N, T, H, W, ci)
         _, ph, _ = A.same_pad(H, 3, self.stride)
         _, pw, _ = A.same_pad(W, 3, self.stride)
-        ops.Profiler.tag = "b"
-        b, partial = ops.dw_fwd(a, d["wb"], d["bb"], self.stride, ph, pw, self.has_se)
-        del a
+        if tc and Options.fuse_expand and x.dtype == torch.bfloat16 and \
+                ops.expand_dw_supported(T, H, W, x.shape[-1], ci, self.stride) > 0:
+            ops.Profiler.tag = "ab"
+            b, partial = ops.expand_dw_fwd(x, d["a"].wp, d["a"].bias, d["wb"], d["bb"],
+                                           self.stride, ph, pw, self.has_se)
+        else:
+            ops.Profiler.tag = "a"
+            a = d["a"].run(x, N * T * H * W, use_tc=tc, relu=True).view(N, T, H, W, ci)
+            ops.Profiler.tag = "b"
+            b, partial = ops.dw_fwd(a, d["wb"], d["bb"], self.stride, ph, pw, self.has_se)
+            del a
         _, _, Ho, Wo, _ = b.shape
         se = None
         if self.has_se:
