@@ -11,9 +11,10 @@ ap.add_argument("what", nargs="?", default="all")
 ap.add_argument("--size", type=int, default=224)
 ap.add_argument("--clips", type=int, default=8)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--T", type=int, default=16)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
-N, T, S0 = a.clips, 16, a.size // 2
+N, T, S0 = a.clips, a.T, a.size // 2
 g = torch.Generator(device=dev); g.manual_seed(0)
 def rnd(*shape, dtype=torch.bfloat16): return torch.randn(*shape, generator=g, device=dev, dtype=torch.float32).to(dtype)
 def timeit(name, fn, bytes_):
@@ -38,6 +39,19 @@ for si, (Hin, cin, inner, cout) in enumerate(stages):
             for se in (True,):
                 timeit(f"dw s{si+2} {H}x{H}x{ci} stride{stride}", lambda: ops.dw_fwd(x, w, b, stride, ph, ph, se),
                        (x.numel() + N * T * Ho * Ho * ci) * 2)
+        if a.what in ("ab", "all"):
+            cin_s = pad8(cin if stride == 2 else cout)
+            x = rnd(N, T, H, H, cin_s); w = rnd(27, ci, dtype=torch.float32); b = rnd(ci, dtype=torch.float32)
+            wa = rnd((ci + 15) // 16 * 16, (cin_s + 63) // 64 * 64); ba = rnd(ci, dtype=torch.float32)
+            _, ph, _ = same_pad(H, 3, stride)
+            if ops.expand_dw_supported(T, H, H, cin_s, ci, stride) > 0:
+                timeit(f"ab s{si+2} {H}x{H} {cin_s}->{ci} stride{stride}", lambda: ops.expand_dw_fwd(x, wa, ba, w, b, stride, ph, ph, True),
+                       (x.numel() + N * T * Ho * Ho * ci) * 2)
+            M = N * T * H * H
+            timeit(f"  (a alone: M={M} K={cin_s} N={ci})", lambda: ops.pw_tc_fwd(x.view(M, cin_s), wa, ba, M=M, K=cin_s, Nc=ci, relu=True),
+                   (x.numel() + M * ci) * 2)
+            xx = rnd(N, T, H, H, ci)
+            timeit(f"  (b alone)", lambda: ops.dw_fwd(xx, w, b, stride, ph, ph, True), (xx.numel() + N * T * Ho * Ho * ci) * 2)
         if a.what in ("pw", "all") and stride == 1:
             M = N * T * H * H
             xa = rnd(M, pad8(cin if False else cout)); K = xa.shape[1]

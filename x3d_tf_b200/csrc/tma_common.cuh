@@ -38,6 +38,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > kSpinLimit) __trap();      // a lost arrival must fail the launch, not hang the GPU
   }
 }
+// Same wait, but each poll may stay suspended in hardware for up to `ns` nanoseconds: a waiting
+// warp then costs (almost) no issue slots, which matters when it shares a scheduler with warps
+// that are issue-bound (the stencil warps).
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity, uint32_t ns = 20000u) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(ns)
+        : "memory");
+    if (done) break;
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+// Lean wait for hot loops: one try_wait + one branch on the fast path, the spin counter only on
+// the slow path (a lost arrival still traps instead of hanging the GPU).
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni DONE_%=;\n\t"
+      "mov.u32 n, 0;\n"
+      "SPIN_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni DONE_%=;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 q, n, %2;\n\t"
+      "@q bra.uni SPIN_%=;\n\t"
+      "trap;\n"
+      "DONE_%=:\n\t}"
+      ::"r"(addr), "r"(parity), "r"(kSpinLimit)
+      : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

@@ -20,6 +20,8 @@
 //      rotating accumulator sets), pack the finished output frame t-1 into a staging buffer and
 //      the copy lane TMA-stores it.
 // Hand-over between the roles is by mbarriers only; the frame loop has no __syncthreads.
+#include <stdlib.h>
+
 #include "tma_common.cuh"
 
 namespace x3d {
@@ -27,7 +29,9 @@ namespace abf {
 
 using namespace ptx;
 
-constexpr int kRing = 2;      // frame ring, A ring and output staging depth
+constexpr int kRing = 2;      // A ring and output staging depth (index math below assumes 2)
+constexpr int kFrames = 3;    // frame ring depth: frame t+1 is drained while frame t is read
+constexpr int kStoreLag = 3;  // the copy lane stores frame t-3 in iteration t (never waits on the step in flight)
 
 __device__ __forceinline__ void tcgen05_before_sync() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -60,10 +64,10 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 // K-major operand, 128-byte swizzle, 8-row atoms stacked every 1024 B (same as x3d_pw_tc.cu).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t sbo = 1024) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
@@ -100,6 +104,7 @@ struct Params {
   int slot_bytes;        // frame ring slot
   int stage_bytes;       // output staging buffer
   int off_wa, off_a, off_ring, off_stage, off_red, off_w2, off_bias;   // from the 1024-aligned base
+  int dbg;               // X3D_ABF_DEBUG experiments (0 in production)
 };
 
 template <typename T> struct Elem;
@@ -112,9 +117,13 @@ template <> struct Elem<float> {
 };
 template <> struct Elem<bf16> {
   static __device__ __forceinline__ float2 lds2(uint32_t a) {
-    uint32_t u;
+    // byte permutes keep the unpack on the ALU pipe (ptxas turns `u << 16` into an IMAD, which
+    // would compete with the FFMA2 stream for the FMA pipe)
+    uint32_t u, lo, hi;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(a));
-    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+    asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(lo) : "r"(u));
+    asm("prmt.b32 %0, %1, 0, 0x3244;" : "=r"(hi) : "r"(u));
+    return make_float2(__uint_as_float(lo), __uint_as_float(hi));
   }
 };
 __device__ __forceinline__ void sts2_f32(uint32_t a, float2 v) {
@@ -149,9 +158,9 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint64_t* a_empty = a_full + kRing;                       // [2] MMAs reading the stage retired
   uint64_t* acc_full = a_empty + kRing;                     // [2] TMEM accumulator complete
   uint64_t* acc_empty = acc_full + 2;                       // [2] TMEM accumulator drained
-  uint64_t* ring_full = acc_empty + 2;                      // [2] frame written by every warp
-  uint64_t* ring_empty = ring_full + kRing;                 // [2] frame read by every warp
-  uint64_t* staged = ring_empty + kRing;                    // [2] output frame packed
+  uint64_t* ring_full = acc_empty + 2;                      // [3] frame written by every warp
+  uint64_t* ring_empty = ring_full + kFrames;               // [3] frame read by every warp
+  uint64_t* staged = ring_empty + kFrames;                  // [2] output frame packed
   uint64_t* sfree = staged + kRing;                         // [2] TMA store has read the buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfree + kRing);
   const uint32_t wa_s = smem_s + p.off_wa;
@@ -160,7 +169,9 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t stage_s = smem_s + p.off_stage;
   float* s_red = reinterpret_cast<float*>(smem + p.off_red);
   const uint32_t w2_s = smem_s + p.off_w2;
-  float* s_bias = reinterpret_cast<float*>(smem + p.off_bias);
+  // bias as a GEMM operand: ones[128 x 16] (one 8-row atom, SBO = 0) x  [hi(shift), lo(shift)] rows
+  const uint32_t ones_s = smem_s + p.off_bias;               // 1 KiB atom
+  const uint32_t biasop_s = ones_s + 1024;                   // [CHN rows x 128 B], 128B swizzle
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -176,8 +187,27 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int BH = (p.Q - 1) * S + 3;
   const int n_acc = p.MB == 1 ? 2 : 1;                      // TMEM accumulator buffers
 
-  for (int i = tid; i < p.CHN; i += blockDim.x)
-    s_bias[i] = (c0 + i < p.Cs) ? p.bias_a[c0 + i] : 0.f;
+  // The BN shift of bn_a enters the accumulator through the tensor core as well: D = ones x Bop
+  // with ones[m, 0:2] = 1 and Bop[n, 0:2] = (hi, lo) bf16 split of shift[n] (exact to 2^-17), so
+  // the drain does no floating-point add at all.  Both tiles are K-major, 128B-swizzled: the
+  // 16-byte chunk j of row r sits at chunk position j ^ (r % 8).
+  for (int i = tid; i < 8 + p.CHN; i += blockDim.x) {
+    const bool is_one = i < 8;
+    const int r = is_one ? i : i - 8;
+    const uint32_t row_s = (is_one ? ones_s : biasop_s) + static_cast<uint32_t>(r) * 128u;
+    uint32_t w0 = 0x3f803f80u;                                 // (1.0, 1.0) bf16
+    if (!is_one) {
+      const float b = (c0 + r < p.Cs) ? p.bias_a[c0 + r] : 0.f;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+      w0 = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo)) << 16);
+    }
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t a = row_s + static_cast<uint32_t>((j ^ (r & 7)) * 16);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(j == 0 ? w0 : 0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+    }
+  }
+  fence_proxy_async();                                         // generic writes -> tensor-core (async proxy) reads
   if (tid == 0) {
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmW);
@@ -188,10 +218,12 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_init(&a_empty[s], 1);
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], static_cast<uint32_t>(p.cwarps));
-      mbar_init(&ring_full[s], static_cast<uint32_t>(p.cwarps));
-      mbar_init(&ring_empty[s], static_cast<uint32_t>(p.cwarps));
       mbar_init(&staged[s], static_cast<uint32_t>(p.cwarps));
       mbar_init(&sfree[s], 1);
+    }
+    for (int s = 0; s < kFrames; ++s) {
+      mbar_init(&ring_full[s], static_cast<uint32_t>(p.cwarps));
+      mbar_init(&ring_empty[s], static_cast<uint32_t>(p.cwarps));
     }
     fence_barrier_init();
   }
@@ -215,7 +247,7 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int kc = 0; kc < p.KC; ++kc)
         tma_load_2d_s(wa_s + kc * w_chunk_bytes, &tmW, kc * 64, c0, w_full);
       auto load_x = [&](int f) {
-        const int s = f % kRing;
+        const int s = f & 1;
         mbar_expect_tx(&a_full[s], static_cast<uint32_t>(p.KC * p.a_box_bytes));
         for (int kc = 0; kc < p.KC; ++kc)
           tma_load_5d(a_s + s * p.a_stage_bytes + kc * p.a_kc_bytes, &tmX, kc * 64, wi0, hi0, f, n,
@@ -225,57 +257,61 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const uint32_t idesc = make_idesc_bf16(p.CHN);
       mbar_wait(w_full, 0);
       auto store_frame = [&](int f) {
-        const int k = f % kRing;
-        mbar_wait(&staged[k], static_cast<uint32_t>((f / kRing) & 1));
+        const int k = f & 1;
+        mbar_wait_lean(&staged[k], static_cast<uint32_t>((f >> 1) & 1));
         tma_store_5d(&tmOut, stage_s + k * p.stage_bytes, c0, wo0, ho0, f, n);
         tma_store_commit();
-        tma_store_wait_read<1>();            // the store of frame f-1 has drained its buffer
-        if (f >= 1) mbar_arrive(&sfree[(f - 1) % kRing]);
+        // never wait for the store just issued: only for the previous one (a whole step old), whose
+        // staging buffer is the one the compute warps pack next
+        tma_store_wait_read<1>();
+        if (f >= 1) mbar_arrive(&sfree[(f - 1) & 1]);
       };
       for (int t = 0; t < p.T; ++t) {
-        const int s = t % kRing;
-        const int b = t % n_acc;
-        mbar_wait(&a_full[s], static_cast<uint32_t>((t / kRing) & 1));
-        mbar_wait(&acc_empty[b], static_cast<uint32_t>(((t / n_acc) & 1) ^ 1));
+        const int s = t & 1;
+        const int b = n_acc == 2 ? (t & 1) : 0;
+        mbar_wait_lean(&a_full[s], static_cast<uint32_t>((t >> 1) & 1));
+        mbar_wait_lean(&acc_empty[b], static_cast<uint32_t>((n_acc == 2 ? (t >> 1) & 1 : t & 1) ^ 1));
         tcgen05_after_sync();
         const uint32_t a_base = a_s + s * p.a_stage_bytes;
-        for (int mb = 0; mb < p.MB; ++mb) {
+        for (int mb = 0; mb < ((p.dbg & 2) ? 0 : p.MB); ++mb) {
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b * 128 + mb * p.CHN);
+          umma_bf16(d_tmem, make_desc_sw128(ones_s, 0), make_desc_sw128(biasop_s), idesc, 0u);
           for (int k = 0; k < p.k16; ++k) {
             const int kc = k >> 2, kk = k & 3;
             umma_bf16(d_tmem, make_desc_sw128(a_base + kc * p.a_kc_bytes + mb * 16384 + kk * 32),
-                      make_desc_sw128(wa_s + kc * w_chunk_bytes + kk * 32), idesc, k != 0 ? 1u : 0u);
+                      make_desc_sw128(wa_s + kc * w_chunk_bytes + kk * 32), idesc, 1u);
           }
         }
         umma_commit(&a_empty[s]);
         umma_commit(&acc_full[b]);
         if (t + kRing < p.T) {               // refill the A stage as soon as its MMAs have retired
-          mbar_wait(&a_empty[s], static_cast<uint32_t>((t / kRing) & 1));
+          mbar_wait_lean(&a_empty[s], static_cast<uint32_t>((t >> 1) & 1));
           load_x(t + kRing);
         }
-        if (t >= 2) store_frame(t - 2);
+        if (t >= kStoreLag) store_frame(t - kStoreLag);
       }
-      if (p.T >= 2) store_frame(p.T - 2);
-      store_frame(p.T - 1);
+      for (int f = (p.T > kStoreLag ? p.T - kStoreLag : 0); f < p.T; ++f) store_frame(f);
       tma_store_wait_read<0>();              // shared memory must outlive the bulk stores
     }
   } else {
     // ------------------------------------------------------------ compute warps
-    float2 wr[18];
+    // dt=0 taps stay in registers; the dt=1 and dt=2 taps are read from shared memory ([18][C2]
+    // float2, conflict-free) so that the TMEM drain fits in the 128-register budget without spills
+    float2 wr[9];
     float2 bia = make_float2(0.f, 0.f);
     if (on) {
 #pragma unroll
-      for (int i = 0; i < 18; ++i) wr[i] = ld2(p.w + i * p.Cs + c);
+      for (int i = 0; i < 9; ++i) wr[i] = ld2(p.w + i * p.Cs + c);
       bia = ld2(p.bias + c);
     } else {
 #pragma unroll
-      for (int i = 0; i < 18; ++i) wr[i] = make_float2(0.f, 0.f);
+      for (int i = 0; i < 9; ++i) wr[i] = make_float2(0.f, 0.f);
     }
     const uint32_t w2_t = w2_s + static_cast<uint32_t>(cp) * 8;
     if (slot == 0) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const float2 w = (c < p.Cs) ? ld2(p.w + (18 + i) * p.Cs + c) : make_float2(0.f, 0.f);
+      for (int i = 0; i < 18; ++i) {
+        const float2 w = (c < p.Cs) ? ld2(p.w + (9 + i) * p.Cs + c) : make_float2(0.f, 0.f);
         sts2_f32(w2_t + i * (C2 * 8), w);
       }
     }
@@ -295,6 +331,7 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     int ncol = p.Wo - wo0;
     if (ncol > SW) ncol = SW;
     const bool lane0 = lane == 0;
+    const bool on_se = on && p.partial != nullptr;
 
     // ---- TMEM drain assignment: lane quarter q = warp % 4; the warps that share a quarter split
     // the CHN columns in groups of 8.
@@ -305,44 +342,70 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int g_lo = groups * me / peers, g_hi = groups * (me + 1) / peers;
     const int npix = BH * BW;
 
-    auto drain = [&](int t) {
-      const int b = t % n_acc;
-      const int rs = t % kRing;
-      mbar_wait(&acc_full[b], static_cast<uint32_t>((t / n_acc) & 1));
+    // per-thread pixel bookkeeping of the drain, once per CTA: for pixel block mb this lane owns halo
+    // pixel r = mb*128 + q*32 + lane; bit mb of pix_m = it exists, of in_m = it is inside the image
+    uint32_t pix_m = 0, in_m = 0;
+    int mb_n = 0;                                              // pixel blocks this lane quarter touches
+    for (int mb = 0; mb < p.MB; ++mb) {
+      if (mb * 128 + q * 32 >= npix) break;
+      mb_n = mb + 1;
+      const int r = mb * 128 + q * 32 + lane;
+      const int hh = r / BW, ww = r - hh * BW;
+      if (r < npix) {
+        pix_m |= 1u << mb;
+        if (static_cast<unsigned>(hi0 + hh) < static_cast<unsigned>(p.H) &&
+            static_cast<unsigned>(wi0 + ww) < static_cast<unsigned>(p.W))
+          in_m |= 1u << mb;
+      }
+    }
+    const uint32_t drain_off = static_cast<uint32_t>(q * 32 + lane) * PS + static_cast<uint32_t>(g_lo) * 16;
+    const uint32_t drain_tm = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g_lo * 8);
+
+    auto emit8 = [&](uint32_t dst, bool inside, bool pix, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                     uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7) {
+      uint32_t o0, o1, o2, o3;
+      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o0) : "f"(__uint_as_float(a1)), "f"(__uint_as_float(a0)));
+      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o1) : "f"(__uint_as_float(a3)), "f"(__uint_as_float(a2)));
+      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o2) : "f"(__uint_as_float(a5)), "f"(__uint_as_float(a4)));
+      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o3) : "f"(__uint_as_float(a7)), "f"(__uint_as_float(a6)));
+      if (inside)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+      else if (pix)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+    };
+
+    // Index arithmetic is shifts and masks only (IMAD-based div/mod would sit on the FMA pipe the
+    // stencil saturates): frame t = 3*k3 + rs with rs known at compile time in the unrolled loop.
+    auto drain = [&](int t, int rs, int k3) {
+      const int b = n_acc == 2 ? (t & 1) : 0;
+      const uint32_t acc_par = static_cast<uint32_t>(n_acc == 2 ? (t >> 1) & 1 : t & 1);
+      mbar_wait_lean(&acc_full[b], acc_par);
       tcgen05_after_sync();
-      if (t >= kRing) mbar_wait(&ring_empty[rs], static_cast<uint32_t>((t / kRing - 1) & 1));
-      const uint32_t slot_base = ring_s + rs * p.slot_bytes;
-      for (int mb = 0; mb < p.MB; ++mb) {
-        const int r = mb * 128 + q * 32 + lane;              // pixel of the halo tile
-        const int hh = r / BW, ww = r - hh * BW;
-        const bool pix = r < npix;
-        const bool inside = pix && static_cast<unsigned>(hi0 + hh) < static_cast<unsigned>(p.H) &&
-                            static_cast<unsigned>(wi0 + ww) < static_cast<unsigned>(p.W);
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                               static_cast<uint32_t>(b * 128 + mb * p.CHN);
-        const uint32_t dst = slot_base + static_cast<uint32_t>(r) * PS;
-        for (int g = g_lo; g < g_hi; ++g) {
-          uint32_t v[8];
-          tmem_ld8(taddr + g * 8, v);
+      if (k3 >= 1) mbar_wait_lean(&ring_empty[rs], static_cast<uint32_t>((k3 & 1) ^ 1));
+      const uint32_t slot_base = ring_s + rs * p.slot_bytes + drain_off;
+      for (int mb = 0; mb < ((p.dbg & 1) ? 0 : mb_n); ++mb) {
+        const bool pix = (pix_m >> mb) & 1u, inside = (in_m >> mb) & 1u;
+        const uint32_t taddr = drain_tm + static_cast<uint32_t>(b * 128 + mb * p.CHN);
+        const uint32_t dst = slot_base + static_cast<uint32_t>(mb * 128) * PS;
+        int g = g_lo;
+        for (; g + 1 < g_hi; g += 2) {
+          uint32_t v[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                "=r"(v[14]), "=r"(v[15])
+              : "r"(taddr + (g - g_lo) * 8));
           tmem_ld_wait();
-          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + g * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + g * 8 + 4);
-          float2 y[4];
-          y[0] = __fadd2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(b0.x, b0.y));
-          y[1] = __fadd2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(b0.z, b0.w));
-          y[2] = __fadd2_rn(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(b1.x, b1.y));
-          y[3] = __fadd2_rn(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(b1.z, b1.w));
-          uint32_t o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t u;
-            asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(y[j].y), "f"(y[j].x));
-            o[j] = inside ? u : 0u;
-          }
-          if (pix)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + g * 16), "r"(o[0]),
-                         "r"(o[1]), "r"(o[2]), "r"(o[3])
-                         : "memory");
+          emit8(dst + (g - g_lo) * 16, inside, pix, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+          emit8(dst + (g - g_lo) * 16 + 16, inside, pix, v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+        }
+        if (g < g_hi) {
+          uint32_t v[8];
+          tmem_ld8(taddr + (g - g_lo) * 8, v);
+          tmem_ld_wait();
+          emit8(dst + (g - g_lo) * 16, inside, pix, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
         }
       }
       tcgen05_before_sync();
@@ -354,14 +417,14 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     };
 
     auto stage_out = [&](float2 (&A)[SW], int t_out) {
-      const int k = t_out % kRing;
-      if (t_out >= kRing) mbar_wait(&sfree[k], static_cast<uint32_t>((t_out / kRing - 1) & 1));
+      const int k = t_out & 1;
+      if (t_out >= kRing) mbar_wait_lean(&sfree[k], static_cast<uint32_t>(((t_out >> 1) & 1) ^ 1));
       const uint32_t dst = stage_s + k * p.stage_bytes + soff;
       if (in_slot) {
 #pragma unroll
         for (int j = 0; j < SW; ++j) sts2_bf16(dst + j * OPS, A[j]);
       }
-      if (on) {
+      if (on_se) {
 #pragma unroll
         for (int j = 0; j < SW; ++j)
           if (j < ncol) ssum = __fadd2_rn(ssum, A[j]);
@@ -371,16 +434,19 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (lane0) mbar_arrive(&staged[k]);
     };
 
-    auto step = [&](int t, float2 (&A0)[SW], float2 (&A1)[SW], float2 (&A2)[SW]) {
-      drain(t);
-      const int rs = t % kRing;
-      mbar_wait(&ring_full[rs], static_cast<uint32_t>((t / kRing) & 1));
+    auto step = [&](int t, int rs, int k3, float2 (&A0)[SW], float2 (&A1)[SW], float2 (&A2)[SW]) {
+      // next frame first: its hand-over is never waited for
+      if (t + 1 < p.T) drain(t + 1, rs == 2 ? 0 : rs + 1, rs == 2 ? k3 + 1 : k3);
+      mbar_wait_lean(&ring_full[rs], static_cast<uint32_t>(k3 & 1));
       const uint32_t base = ring_s + rs * p.slot_bytes + toff;
 #pragma unroll
       for (int dh = 0; dh < 3; ++dh) {
-        float2 w2[3];
+        float2 w1[3], w2[3];
 #pragma unroll
-        for (int dw = 0; dw < 3; ++dw) w2[dw] = Elem<float>::lds2(w2_t + (dh * 3 + dw) * (C2 * 8));
+        for (int dw = 0; dw < 3; ++dw) {
+          w1[dw] = Elem<float>::lds2(w2_t + (dh * 3 + dw) * (C2 * 8));
+          w2[dw] = Elem<float>::lds2(w2_t + (9 + dh * 3 + dw) * (C2 * 8));
+        }
 #pragma unroll
         for (int jj = 0; jj < BW; ++jj) {
           const float2 x = Elem<bf16>::lds2(base + dh * RS + jj * PS);
@@ -389,8 +455,8 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const int jn = jj - dw;
             if (jn >= 0 && jn % S == 0 && jn / S < SW) {
               const int j = jn / S;
-              A0[j] = fma2(x, wr[(0 * 3 + dh) * 3 + dw], (dh == 0 && dw == 0) ? bia : A0[j]);
-              A1[j] = fma2(x, wr[(1 * 3 + dh) * 3 + dw], A1[j]);
+              A0[j] = fma2(x, wr[dh * 3 + dw], (dh == 0 && dw == 0) ? bia : A0[j]);
+              A1[j] = fma2(x, w1[dw], A1[j]);
               A2[j] = fma2(x, w2[dw], A2[j]);
             }
           }
@@ -401,10 +467,11 @@ ab_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (t >= 1) stage_out(A2, t - 1);
     };
 
-    for (int t = 0; t < p.T; t += 3) {
-      step(t, acc[1], acc[0], acc[2]);
-      if (t + 1 < p.T) step(t + 1, acc[2], acc[1], acc[0]);
-      if (t + 2 < p.T) step(t + 2, acc[0], acc[2], acc[1]);
+    drain(0, 0, 0);
+    for (int t = 0, k3 = 0; t < p.T; t += 3, ++k3) {
+      step(t, 0, k3, acc[1], acc[0], acc[2]);
+      if (t + 1 < p.T) step(t + 1, 1, k3, acc[2], acc[1], acc[0]);
+      if (t + 2 < p.T) step(t + 2, 2, k3, acc[0], acc[2], acc[1]);
     }
     {
       const int r = (p.T - 1) % 3;
@@ -461,7 +528,7 @@ static Plan make_plan(int H, int W, int Cin, int Cs, int stride, int max_smem) {
   for (int ci = 0; ci < 3; ++ci) {
     for (int si = 0; si < nsw; ++si) {
       const int CH = chs[ci], SW = stride == 1 ? sws1[si] : sws2[si];
-      int qmax = 224 / (CH / 2);
+      int qmax = 224 / (CH / 2);                     // <= 7 compute warps + the copy warp
       if (qmax > 9) qmax = 9;
       if (qmax > Ho) qmax = Ho;
       for (int Q = qmax; Q >= 1; --Q) {
@@ -489,11 +556,12 @@ static Plan make_plan(int H, int W, int Cin, int Cs, int stride, int max_smem) {
         pl.off_wa = off;   off += pl.KC * pl.CHN * 128;
         off = (off + 1023) / 1024 * 1024;
         pl.off_a = off;    off += kRing * pl.a_stage_bytes;
-        pl.off_ring = off; off += kRing * pl.slot_bytes;
+        pl.off_ring = off; off += kFrames * pl.slot_bytes;
         pl.off_stage = off; off += kRing * pl.stage_bytes;
         pl.off_red = off;  off += 9 * CH * 4;
-        pl.off_w2 = off;   off += 9 * CH * 4;
-        pl.off_bias = off; off += pl.CHN * 4;
+        pl.off_w2 = off;   off += 27 * CH * 4;
+        off = (off + 1023) / 1024 * 1024;
+        pl.off_bias = off; off += 1024 + pl.CHN * 128;   // ones atom + bias operand tile
         // the last pixel block of an MMA always reads 128 rows: keep that inside the allocation
         const int mma_end = pl.off_a + kRing * pl.a_stage_bytes - pl.a_kc_bytes + pl.MB * 16384;
         if (off < mma_end) off = mma_end;
@@ -624,6 +692,7 @@ extern "C" int x3d_expand_dw_fwd(const void* x, const void* wa, const float* bia
   p.slot_bytes = pl.slot_bytes; p.stage_bytes = pl.stage_bytes;
   p.off_wa = pl.off_wa; p.off_a = pl.off_a; p.off_ring = pl.off_ring; p.off_stage = pl.off_stage;
   p.off_red = pl.off_red; p.off_w2 = pl.off_w2; p.off_bias = pl.off_bias;
+  { const char* e = getenv("X3D_ABF_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return stride == 1 ? abf::dispatch<1>(tx, tw, to, p, pl, N, st) : abf::dispatch<2>(tx, tw, to, p, pl, N, st);
 }

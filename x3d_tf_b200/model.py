@@ -227,7 +227,10 @@ class PointwiseConv:
 class Options:
     pointwise = "tc"          # "tc": tcgen05 kernel for bf16 activations; "simt": CUDA-core GEMM
     stem = "tc"               # "tc": tcgen05 implicit-GEMM stem for bf16 activations; "simt"
-    fuse_expand = True        # bf16 + "tc": run a/bn_a/relu/b/bn_b as ONE kernel (x3d_expand_dw_fwd)
+    # bf16 + "tc": run a/bn_a/relu/b/bn_b as ONE kernel (x3d_expand_dw_fwd).  Parity-green, but on
+    # B200 it is only break-even with the two-kernel path today (profiles/r01_fused_expand_dw.md),
+    # so it is opt-in.
+    fuse_expand = False
 
 
 def _use_tc() -> bool:
