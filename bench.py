@@ -316,9 +316,19 @@ def run_b200(args):
         b_bytes = work["b"]["bytes"] * clips
         kname = "dw_tma_kernel (channelwise 3x3x3 + BN + SE sums)"
     achieved = b_bytes / (b["ms"] * 1e-3) / 1e9
+    # DRAM bytes per launch of the same kernel from the committed ncu capture (read + write,
+    # averaged over the launches of one step, like `achieved`); null if no capture matches
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_dw_traffic.json")
+    if not fused and os.path.exists(tp):
+        with open(tp) as f:
+            td = json.load(f)
+        if td.get("workload") == args.workload and td.get("clips") == clips:
+            traffic = td["bytes_per_launch"]
     roofline = {"kernel": kname, "bound": "hbm",
                 "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                "traffic": None, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                "traffic": traffic, "algorithmic_bytes_per_launch": b_bytes / max(b["launches"], 1),
+                "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
                 "launches_per_step": b["launches"],
                 "algorithmic_bytes_per_step": b_bytes,
                 "avg_launch_ms": b["ms"] / max(b["launches"], 1),
