@@ -164,6 +164,71 @@ int x3d_expand_dw_fwd(const void* x, const void* wa, const float* bias_a, const 
                       int W, int Cin, int C, int Kpad, int Npad, int stride, int pad_h, int pad_w,
                       void* stream);
 
+/* ==== Training step (BASELINE configs[4]; train.py:85-152 -> Keras train_step) ================
+ * fp32, channels-last, activations viewed as [M, C] matrices (M = N*T*H*W).  Reductions accumulate
+ * into caller-zeroed fp64 buffers.  The forward convolutions of the training step are the entry
+ * points above called with raw (un-folded) kernels and no bias; what follows is everything else. */
+
+/* Per-channel reductions over rows, one result pair per segment of `seg_rows` rows:
+ *   mode 0: out[s][0][c] += sum a,  out[s][1][c] += sum a^2         (BatchNorm batch statistics)
+ *   mode 1: out[s][0][c] += sum g,  out[s][1][c] += sum g*xhat      (BatchNorm backward;
+ *           g = a masked by relu_out > 0 if relu_out != NULL, xhat = (x - mean) * rstd)
+ *   mode 2: out[s][0][c] += sum a                                    (bias gradients, SE pooling) */
+int x3d_colreduce(const float* a, const float* x, const float* mean, const float* rstd,
+                  const float* relu_out, int64_t M, int C, int64_t seg_rows, double* out, int mode,
+                  void* stream);
+/* BatchNormalization(training=True), model.py:89,196,254,268,300,368: batch mean / biased variance
+ * from the mode-0 sums, rstd = 1/sqrt(var+eps); moving = momentum*moving + (1-momentum)*batch. */
+int x3d_bn_finalize(const double* sums, int64_t M, int C, float eps, float momentum, float* mean,
+                    float* var, float* rstd, float* mov_mean, float* mov_var, void* stream);
+int x3d_bn_apply_fwd(const float* x, const float* mean, const float* rstd, const float* gamma,
+                     const float* beta, float* y, int64_t M, int C, int relu, void* stream);
+/* dx = gamma*rstd*(g - sum_g/M - xhat*sum_gxhat/M) with the mode-1 sums (which are also dbeta, dgamma) */
+int x3d_bn_bwd_apply(const float* dy, const float* x, const float* relu_out, const float* mean,
+                     const float* rstd, const float* gamma, const double* sums, float* dx, int64_t M,
+                     int C, void* stream);
+int x3d_d2f(const double* in, float* out, int64_t n, float scale, void* stream);
+/* Backward-filter of a 1x1x1 conv (a, c, residual, conv5, fc1, fc2, se_fc1, se_fc2):
+ * dW[k,n] += sum_m A[row(m),k] * dD[m,n]; gather/geometry as in x3d_pw_fwd.  (Backward-data is
+ * x3d_pw_fwd with the transposed kernel.) */
+int x3d_pw_wgrad(const float* A, const float* dD, double* dW, int64_t M, int K, int N, int lda,
+                 int ldd, int gather, int Ho, int Wo, int Hi, int Wi, int stride, void* stream);
+/* Backward-data / backward-filter of the channelwise 3x3x3 conv (Bottleneck.b, model.py:259-267) */
+int x3d_dw_dgrad(const float* dy, const float* w, float* dx, int N, int T, int H, int W, int C,
+                 int stride, int pad_h, int pad_w, void* stream);
+int x3d_dw_wgrad(const float* x, const float* dy, double* dwt, int N, int T, int H, int W, int C,
+                 int stride, int pad_h, int pad_w, void* stream);
+/* Stem in training form (model.py:202-208): conv_s and conv_t as separate ops so that the conv_s
+ * output can be kept for conv_t's backward-filter; flip=1 turns x3d_tconv_fwd into backward-data. */
+int x3d_stem_convs_fwd(const float* in, const float* ws, float* out, int N, int T, int H, int W,
+                       int C, void* stream);
+int x3d_stem_convs_wgrad(const float* in, const float* ds, double* dws, int N, int T, int H, int W,
+                         int C, void* stream);
+int x3d_tconv_fwd(const float* in, const float* wt, float* out, int N, int T, int64_t P, int C,
+                  int kt, int flip, void* stream);
+int x3d_tconv_wgrad(const float* s, const float* dy, double* dwt, int N, int T, int64_t P, int C,
+                    int kt, void* stream);
+/* out = swish(y * s[clip,c]) and its backward (dy, ds[clip,c] += sum dv*y), model.py:311-316 */
+int x3d_scale_swish_fwd(const float* y, const float* s, float* out, int64_t M, int C,
+                        int64_t rows_per_clip, void* stream);
+int x3d_scale_swish_bwd(const float* dout, const float* y, const float* s, float* dy, double* ds,
+                        int64_t M, int C, int64_t rows_per_clip, void* stream);
+/* Elementwise: op 0 relu(a+b) | 1 a*(b>0) | 2 sigmoid(a) | 3 a*b*(1-b) | 4 a+b | 5 a*b */
+int x3d_ew(const float* a, const float* b, float* out, int64_t n, int op, void* stream);
+/* Backward of the global average pool (AdaptiveAvgPool3D, model.py:473-483) */
+int x3d_pool_bwd(const float* dm, float* dy, int64_t M, int C, int64_t rows_per_clip, float scale,
+                 int accumulate, void* stream);
+/* Backward-data of the strided shortcut conv: dst[nt, ho*s, wo*s, :] += src[nt, ho, wo, :] */
+int x3d_strided_add(const float* src, float* dst, int NT, int Ho, int Wo, int Hi, int Wi,
+                    int stride, int C, void* stream);
+int x3d_dropout_mask(float* mask, int64_t n, float rate, uint64_t seed, void* stream);
+/* Softmax + SparseCategoricalCrossentropy on probabilities (train.py:104) and d loss / d logits * gscale */
+int x3d_softmax_xent(const float* logits, const int32_t* labels, float* loss, float* dlogits, int N,
+                     int ncls, float gscale, void* stream);
+/* SGD(nesterov=True) + L2, train.py:88-92, model.py:47:  g = grad + wd*w; v = mu*v - lr*g; w += mu*v - lr*g */
+int x3d_sgd_nesterov_step(float* w, const float* grad, float* v, const float* wd, int64_t n,
+                          float lr, float momentum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,126 @@
+"""Parity of the CUDA training step (x3d_tf_b200/training.py, C ABI section "Training step")
+against the float64 torch-autograd oracle (oracle/x3d_train_oracle.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import x3d_oracle as O
+from oracle import x3d_train_oracle as TO
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(variant="X3D_XS", n=2, t=4, s=64, dropout=0.5, seed=3):
+    from x3d_tf_b200.arch import build_arch
+    from x3d_tf_b200.config import get_config
+    from x3d_tf_b200.synth import synthetic_clips, synthetic_weights
+    from x3d_tf_b200.training import X3DTrainer
+    cfg = get_config(variant, freeze=False)
+    cfg.NETWORK.DROPOUT_RATE = dropout
+    cfg.freeze()
+    W = synthetic_weights(build_arch(cfg), seed=seed)
+    x = synthetic_clips(n, t, s, s, cfg.DATA.MEAN, cfg.DATA.STD, seed=seed + 1)
+    rng = np.random.default_rng(seed + 2)
+    labels = rng.integers(0, cfg.NETWORK.NUM_CLASSES, size=n).astype(np.int32)
+    mask = None
+    if dropout > 0:
+        mask = ((rng.random((n, 2048)) >= dropout) / (1.0 - dropout)).astype(np.float32)
+    torch.cuda.set_device(0)
+    tr = X3DTrainer(cfg).load(W)
+    if mask is not None:
+        tr.fixed_dropout_mask = torch.from_numpy(mask).cuda()
+    return cfg, W, x, labels, mask, tr
+
+
+def _rel(got, want):
+    want = np.asarray(want, np.float64)
+    return float(np.abs(np.asarray(got, np.float64) - want).max() / max(np.abs(want).max(), 1e-12))
+
+
+def _l2(got, want):
+    want = np.asarray(want, np.float64)
+    return float(np.linalg.norm(np.asarray(got, np.float64) - want) / max(np.linalg.norm(want), 1e-30))
+
+
+@pytest.mark.parametrize("variant,n,s", [("X3D_XS", 2, 64), ("X3D_S", 2, 91)])
+def test_training_step_matches_autograd_oracle(variant, n, s):
+    """loss, every gradient, the SGD-Nesterov update and the moving statistics of ONE step against
+    float64 autograd.
+
+    ReLU is a kink: the fp32 forward differs from the float64 one by ~4e-5 of the activation scale,
+    so a few pre-activations that close to zero get a different sign in the two runs (measured: 1
+    of 13 824 conv5 outputs), and then the two gradients are gradients at different branches.  The
+    oracle is therefore told which branch the CUDA run took at every ReLU (`relu_masks`); with
+    that, every gradient must agree to 1e-3 of its tensor's largest value.  A second pass without
+    the masks bounds the effect of the flips (0.25 in the L2 norm; ~7e-2 worst case measured at this
+    tiny batch, where one flip is 1/32 of a channel's statistics)."""
+    cfg, W, x, labels, mask, tr = _setup(variant, n=n, s=s)
+    tr.relu_masks = []
+    lr, wd = 0.05, float(cfg.NETWORK.WEIGHT_DECAY)
+    loss = tr.step(torch.from_numpy(x).cuda(), torch.from_numpy(labels).cuda(), lr)
+    torch.cuda.synchronize()
+    spec = O.OracleSpec.from_cfg(cfg)
+    ref = TO.train_step(W, spec, x, labels, lr=lr, momentum=0.9, weight_decay=wd, dropout_mask=mask,
+                        relu_masks=tr.relu_masks)
+    free = TO.train_step(W, spec, x, labels, lr=lr, momentum=0.9, weight_decay=wd, dropout_mask=mask)
+    assert _rel(tr.last_logits.cpu().numpy(), free["logits"]) < 1e-4
+    assert abs(float(loss.mean().item()) - free["loss"]) < 1e-4 * max(1.0, abs(free["loss"]))
+    G = tr.grads()
+    bad, loose = [], []
+    for k, g_ref in ref["grads"].items():
+        got = G[k].astype(np.float64)
+        if TO.is_regularised(k):
+            got = got + 2.0 * wd * W[k]
+        if _rel(got, g_ref) > 1e-3:
+            bad.append((k, _rel(got, g_ref)))
+        if _l2(got, free["grads"][k]) > 0.25:
+            loose.append((k, _l2(got, free["grads"][k])))
+    assert not bad, bad[:10]
+    assert not loose, loose[:10]
+    Wn = tr.weights()
+    bad = [(k, _rel(Wn[k], v)) for k, v in ref["weights"].items() if _rel(Wn[k], v) > 1e-4]
+    assert not bad, bad[:10]
+
+
+def test_two_steps_keep_momentum_and_padding_clean():
+    """The second step starts from the weights AND the velocity of the first; padded channels stay
+    exactly zero.  (The oracle's second step is evaluated at the CUDA run's own step-1 state: on
+    this tiny synthetic batch the loss surface is so rough that two float64 gradients taken 1e-6
+    apart in weight space already differ by >5 %, so independent two-step trajectories cannot be
+    compared.)"""
+    cfg, W, x, labels, mask, tr = _setup("X3D_XS", dropout=0.0)
+    spec = O.OracleSpec.from_cfg(cfg)
+    wd = float(cfg.NETWORK.WEIGHT_DECAY)
+    xd, ld = torch.from_numpy(x).cuda(), torch.from_numpy(labels).cuda()
+    tr.step(xd, ld, 1e-2)
+    torch.cuda.synchronize()
+    W1, V1 = tr.weights(), tr.velocity()
+    assert max(float(np.abs(v).max()) for v in V1.values()) > 0
+    tr.relu_masks = []
+    tr.step(xd, ld, 5e-3)
+    torch.cuda.synchronize()
+    r2 = TO.train_step(W1, spec, x, labels, lr=5e-3, weight_decay=wd, velocity=V1, relu_masks=tr.relu_masks)
+    W2 = tr.weights()
+    bad = []
+    for k, v in r2["weights"].items():
+        if k.endswith("moving_mean") or k.endswith("moving_variance"):
+            continue
+        e = _l2(W2[k].astype(np.float64) - W1[k], v - W1[k])       # displacement of step 2
+        if e > 1e-2:
+            bad.append((k, e))
+    assert not bad, bad[:10]
+    # the displacement contains the 0.9 * (0.9 * v1) momentum carry-over
+    k = "fc2/kernel"
+    no_mom = -5e-3 * 1.9 * r2["grads"][k]
+    assert _l2(W2[k].astype(np.float64) - W1[k], no_mom) > 0.2
+    a = tr.P("stages/0/stage/layer_with_weights-0/bottleneck/a/kernel")          # [24, 56], 54 real
+    assert float(a[:, 54:].abs().max().item()) == 0.0
+
+
+def test_dropout_mask_statistics():
+    from x3d_tf_b200._lib import check, lib
+    m = torch.empty(1 << 20, dtype=torch.float32, device="cuda")
+    check(lib().x3d_dropout_mask(m.data_ptr(), m.numel(), 0.5, 12345, torch.cuda.current_stream().cuda_stream))
+    vals = torch.unique(m).cpu().tolist()
+    assert vals == [0.0, 2.0]
+    assert abs(float((m > 0).float().mean().item()) - 0.5) < 5e-3

@@ -137,3 +137,16 @@ def test_config_merges_reference_style_yaml(tmp_path):
     cfg.freeze()
     assert cfg.NETWORK.SCALE_RES2 is True and cfg.NETWORK.WEIGHT_DECAY == 5e-5
     assert cfg.NETWORK.BN.EPS == 1e-5
+
+
+def test_training_lr_schedule_matches_train_py():
+    """train.py:114-125 -- linear warm-up then half-cosine, per epoch."""
+    import math
+    from x3d_tf_b200.config import get_config
+    from x3d_tf_b200.training import lr_schedule
+    cfg = get_config("X3D_M")
+    t = cfg.TRAIN
+    assert lr_schedule(cfg, 0) == pytest.approx(t.WARMUP_LR)
+    assert lr_schedule(cfg, t.WARMUP_EPOCHS) == pytest.approx(t.BASE_LR)
+    e = t.WARMUP_EPOCHS + 10
+    assert lr_schedule(cfg, e) == pytest.approx(t.BASE_LR * 0.5 * (math.cos(math.pi * e / t.EPOCHS) + 1))

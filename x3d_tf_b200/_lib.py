@@ -65,6 +65,27 @@ SIGNATURES = {
                                       C.c_int, C.c_int, C.c_void_p]),
     "x3d_expand_dw_partial_blocks": (C.c_int, [C.c_int] * 6),
     "x3d_expand_dw_fwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 11 + [C.c_void_p]),
+    # ---- training step
+    "x3d_colreduce": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
+    "x3d_bn_finalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float] + [C.c_void_p] * 6),
+    "x3d_bn_apply_fwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "x3d_bn_bwd_apply": (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_int, C.c_void_p]),
+    "x3d_d2f": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
+    "x3d_pw_wgrad": (C.c_int, [C.c_void_p] * 3 + [C.c_int64] + [C.c_int] * 10 + [C.c_void_p]),
+    "x3d_dw_dgrad": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 8 + [C.c_void_p]),
+    "x3d_dw_wgrad": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 8 + [C.c_void_p]),
+    "x3d_stem_convs_fwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]),
+    "x3d_stem_convs_wgrad": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]),
+    "x3d_tconv_fwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "x3d_tconv_wgrad": (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "x3d_scale_swish_fwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int, C.c_int64, C.c_void_p]),
+    "x3d_scale_swish_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int, C.c_int64, C.c_void_p]),
+    "x3d_ew": (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int, C.c_void_p]),
+    "x3d_pool_bwd": (C.c_int, [C.c_void_p] * 2 + [C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_int, C.c_void_p]),
+    "x3d_strided_add": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 7 + [C.c_void_p]),
+    "x3d_dropout_mask": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_uint64, C.c_void_p]),
+    "x3d_softmax_xent": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "x3d_sgd_nesterov_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_float, C.c_float, C.c_void_p]),
     "x3d_head_fc_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }

@@ -1,0 +1,694 @@
+// Training-step kernels (BASELINE.json configs[4]: X3D-M training step), fp32, channels-last.
+// First correct versions: every operation the Keras train_step of the reference performs around
+// the convolutions (train.py:85-152 -> model.py with training=True) as hand-written CUDA --
+// batch-statistics BatchNorm forward/backward, backward-data / backward-filter of the pointwise,
+// channelwise and stem convolutions, SE / swish / ReLU / dropout / pooling backward, softmax
+// cross-entropy, SGD-Nesterov with L2.  They are coalesced and grid-sized for 148 SMs but not yet
+// tuned (DESIGN.md section 9 lists what the tuned versions will fuse).
+//
+// Reductions over the row dimension accumulate per-thread in fp32 over short row runs, then in
+// fp64 through atomicAdd(double): the fp64 sum of <= 2^24 fp32 partials is exact to ~1e-13
+// relative, so results do not depend on the arrival order after rounding to fp32.
+#include "common.cuh"
+
+namespace x3d {
+namespace train {
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+constexpr int kRowsPerBlock = 256;
+
+// ---------------------------------------------------------------- per-channel row reductions
+// mode 0: out[0][c] += sum a,        out[1][c] += sum a*a            (BN statistics)
+// mode 1: out[0][c] += sum g,        out[1][c] += sum g * xhat       (BN backward; g = dy masked
+//         by relu_out > 0 when relu_out != nullptr; xhat = (x - mean) * rstd)
+// mode 2: out[0][c] += sum a                                          (bias gradients)
+// Rows are split in segments of `seg_rows` (one output row pair per segment: per-clip sums).
+__global__ void __launch_bounds__(256)
+colreduce_kernel(const float* __restrict__ a, const float* __restrict__ x, const float* __restrict__ mean,
+                 const float* __restrict__ rstd, const float* __restrict__ relu_out, long M, int C,
+                 long seg_rows, double* __restrict__ out, int mode) {
+  const int cx = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;                       // 8 row lanes
+  const long seg = blockIdx.z;
+  const long r0 = seg * seg_rows + (long)blockIdx.y * kRowsPerBlock;
+  long r1 = r0 + kRowsPerBlock;
+  const long seg_end = (seg + 1) * seg_rows < M ? (seg + 1) * seg_rows : M;
+  if (r1 > seg_end) r1 = seg_end;
+  float s0 = 0.f, s1 = 0.f;
+  if (cx < C) {
+    const float mu = (mode == 1) ? mean[cx] : 0.f, rs = (mode == 1) ? rstd[cx] : 0.f;
+    for (long r = r0 + ry; r < r1; r += 8) {
+      const float v = a[r * C + cx];
+      if (mode == 0) { s0 += v; s1 = fmaf(v, v, s1); }
+      else if (mode == 1) {
+        const float g = (relu_out == nullptr || relu_out[r * C + cx] > 0.f) ? v : 0.f;
+        s0 += g; s1 = fmaf(g, (x[r * C + cx] - mu) * rs, s1);
+      } else s0 += v;
+    }
+  }
+  __shared__ float sh0[8][33], sh1[8][33];
+  sh0[ry][threadIdx.x & 31] = s0; sh1[ry][threadIdx.x & 31] = s1;
+  __syncthreads();
+  if (ry == 0 && cx < C) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int i = 0; i < 8; ++i) { t0 += sh0[i][threadIdx.x]; t1 += sh1[i][threadIdx.x]; }
+    atomicAdd(out + (seg * 2) * C + cx, t0);
+    if (mode != 2) atomicAdd(out + (seg * 2 + 1) * C + cx, t1);
+  }
+}
+
+// BN statistics from the fp64 sums: mean, biased variance (TF BatchNormalization, model.py:89,196,
+// 254,268,300,368 in training mode), rstd = 1/sqrt(var+eps); moving stats updated in place with
+// momentum m: moving = m*moving + (1-m)*batch (configs/default.py:43).
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long M, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ var, float* __restrict__ rstd,
+                                   float* __restrict__ mov_mean, float* __restrict__ mov_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = sums[c] / (double)M;
+  double v = sums[C + c] / (double)M - mu * mu;
+  if (v < 0.0) v = 0.0;
+  mean[c] = (float)mu; var[c] = (float)v; rstd[c] = (float)(1.0 / sqrt(v + (double)eps));
+  if (mov_mean) mov_mean[c] = momentum * mov_mean[c] + (1.f - momentum) * (float)mu;
+  if (mov_var) mov_var[c] = momentum * mov_var[c] + (1.f - momentum) * (float)v;
+}
+
+// y = (x - mean) * rstd * gamma + beta  (+ ReLU)
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
+                long total, int C, int relu) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float v = (x[i] - mean[c]) * rstd[c] * gamma[c] + beta[c];
+    if (relu) v = fmaxf(v, 0.f);
+    y[i] = v;
+  }
+}
+
+// dx = gamma * rstd * (g - sum_g/M - xhat * sum_gx/M),  g = dy masked by relu_out > 0
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ relu_out,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                    const double* __restrict__ sums, float* __restrict__ dx, long total, int C, long M) {
+  const double invM = 1.0 / (double)M;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const float g = (relu_out == nullptr || relu_out[i] > 0.f) ? dy[i] : 0.f;
+    const float xh = (x[i] - mean[c]) * rstd[c];
+    const float sg = (float)(sums[c] * invM), sgx = (float)(sums[C + c] * invM);
+    dx[i] = gamma[c] * rstd[c] * (g - sg - xh * sgx);
+  }
+}
+
+__global__ void d2f_kernel(const double* __restrict__ in, float* __restrict__ out, long n, float scale) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)(in[i] * (double)scale);
+}
+
+// ---------------------------------------------------------------- backward-filter of a 1x1x1 conv
+// dW[k, n] += sum_m A[row(m), k] * dD[m, n]; row(m) as in x3d_pw_fwd (gather for the strided
+// shortcut).  One block = a 32x32 tile of dW over a run of rows; fp32 partial per block, fp64 atomics.
+__global__ void __launch_bounds__(256)
+pw_wgrad_kernel(const float* __restrict__ A, const float* __restrict__ dD, double* __restrict__ dW, long M,
+                int K, int N, int lda, int ldd, long rows_per_block, int gather, int Ho, int Wo, int Hi,
+                int Wi, int stride) {
+  __shared__ float sa[32][33], sd[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const long m0 = (long)blockIdx.z * rows_per_block;
+  long m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 x 32
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};                      // dW[k0 + ty + 8*i][n0 + tx]
+  for (long mb = m0; mb < m1; mb += 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long m = mb + ty + 8 * i;
+      float av = 0.f, dv = 0.f;
+      if (m < m1) {
+        long arow = m;
+        if (gather) {
+          long q = m;
+          const int wo = (int)(q % Wo); q /= Wo;
+          const int ho = (int)(q % Ho); q /= Ho;
+          arow = (q * Hi + (long)ho * stride) * Wi + (long)wo * stride;
+        }
+        if (k0 + tx < K) av = A[arow * lda + k0 + tx];
+        if (n0 + tx < N) dv = dD[m * ldd + n0 + tx];
+      }
+      sa[ty + 8 * i][tx] = av; sd[ty + 8 * i][tx] = dv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const float d = sd[r][tx];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(sa[r][ty + 8 * i], d, acc[i]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty + 8 * i;
+    if (k < K && n0 + tx < N) atomicAdd(dW + (long)k * N + n0 + tx, (double)acc[i]);
+  }
+}
+
+// ---------------------------------------------------------------- channelwise 3x3x3 backward
+// backward-data (gather form): dx[n,t,h,w,c] = sum_taps dy[n, t+1-dt, (h+ph-dh)/s, (w+pw-dw)/s, c] * w[tap,c]
+__global__ void __launch_bounds__(256)
+dw_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int T, int H,
+                int W, int Ho, int Wo, int C, int stride, int ph, int pw, long total) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long q = i / C;
+    const int x = (int)(q % W); q /= W;
+    const int y = (int)(q % H); q /= H;
+    const int t = (int)(q % T);
+    const long n = q / T;
+    float acc = 0.f;
+    for (int dt = 0; dt < 3; ++dt) {
+      const int to = t + 1 - dt;
+      if (to < 0 || to >= T) continue;
+      for (int dh = 0; dh < 3; ++dh) {
+        const int hy = y + ph - dh;
+        if (hy < 0 || hy % stride) continue;
+        const int ho = hy / stride;
+        if (ho >= Ho) continue;
+        for (int dw = 0; dw < 3; ++dw) {
+          const int wx = x + pw - dw;
+          if (wx < 0 || wx % stride) continue;
+          const int wo = wx / stride;
+          if (wo >= Wo) continue;
+          acc = fmaf(dy[(((n * T + to) * Ho + ho) * (long)Wo + wo) * C + c], w[((dt * 3 + dh) * 3 + dw) * C + c], acc);
+        }
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
+// backward-filter: dw[tap,c] += sum over output pixels x[n, t+dt-1, ho*s+dh-ph, wo*s+dw-pw, c] * dy[n,t,ho,wo,c]
+__global__ void __launch_bounds__(256)
+dw_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, double* __restrict__ dwt, int T, int H,
+                int W, int Ho, int Wo, int C, int stride, int ph, int pw, long opix, long pix_per_block) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  const long p0 = (long)blockIdx.y * pix_per_block;
+  long p1 = p0 + pix_per_block;
+  if (p1 > opix) p1 = opix;
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  if (c < C) {
+    for (long p = p0 + ry; p < p1; p += 8) {
+      long q = p;
+      const int wo = (int)(q % Wo); q /= Wo;
+      const int ho = (int)(q % Ho); q /= Ho;
+      const int t = (int)(q % T);
+      const long n = q / T;
+      const float g = dy[p * C + c];
+#pragma unroll
+      for (int dt = 0; dt < 3; ++dt) {
+        const int ti = t + dt - 1;
+#pragma unroll
+        for (int dh = 0; dh < 3; ++dh) {
+          const int hi = ho * stride + dh - ph;
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw) {
+            const int wi = wo * stride + dw - pw;
+            if (ti >= 0 && ti < T && hi >= 0 && hi < H && wi >= 0 && wi < W)
+              acc[(dt * 3 + dh) * 3 + dw] = fmaf(x[(((n * T + ti) * H + hi) * (long)W + wi) * C + c], g, acc[(dt * 3 + dh) * 3 + dw]);
+          }
+        }
+      }
+    }
+  }
+  __shared__ float sh[8][32];
+  for (int tap = 0; tap < 27; ++tap) {
+    sh[ry][threadIdx.x & 31] = acc[tap];
+    __syncthreads();
+    if (ry == 0 && c < C) {
+      double s = 0.0;
+      for (int i = 0; i < 8; ++i) s += sh[i][threadIdx.x];
+      atomicAdd(dwt + (long)tap * C + c, s);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- stem pieces (training form)
+// conv_s: 1x3x3, stride (1,2,2), explicit zero pad 1 on H and W, 3 -> C (model.py:161-184,203-204)
+__global__ void __launch_bounds__(256)
+stem_convs_fwd_kernel(const float* __restrict__ in, const float* __restrict__ ws, float* __restrict__ out, int H,
+                      int W, int Ho, int Wo, int C, long total) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long q = i / C;
+    const int wo = (int)(q % Wo); q /= Wo;
+    const int ho = (int)(q % Ho);
+    const long nt = q / Ho;
+    float acc = 0.f;
+    for (int dh = 0; dh < 3; ++dh) {
+      const int hi = 2 * ho + dh - 1;
+      if (hi < 0 || hi >= H) continue;
+      for (int dw = 0; dw < 3; ++dw) {
+        const int wi = 2 * wo + dw - 1;
+        if (wi < 0 || wi >= W) continue;
+        const float* px = in + ((nt * H + hi) * (long)W + wi) * 3;
+        const float* wk = ws + ((dh * 3 + dw) * 3) * C + c;
+        acc = fmaf(px[0], wk[0], acc); acc = fmaf(px[1], wk[C], acc); acc = fmaf(px[2], wk[2 * C], acc);
+      }
+    }
+    out[i] = acc;
+  }
+}
+// backward-filter of conv_s: dws[(dh*3+dw)*3+ci, c] += sum in[...] * ds[n,t,ho,wo,c]
+__global__ void __launch_bounds__(256)
+stem_convs_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ ds, double* __restrict__ dws, int H,
+                        int W, int Ho, int Wo, int C, long opix, long pix_per_block) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  const long p0 = (long)blockIdx.y * pix_per_block;
+  long p1 = p0 + pix_per_block;
+  if (p1 > opix) p1 = opix;
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  if (c < C) {
+    for (long p = p0 + ry; p < p1; p += 8) {
+      long q = p;
+      const int wo = (int)(q % Wo); q /= Wo;
+      const int ho = (int)(q % Ho);
+      const long nt = q / Ho;
+      const float g = ds[p * C + c];
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh) {
+        const int hi = 2 * ho + dh - 1;
+#pragma unroll
+        for (int dw = 0; dw < 3; ++dw) {
+          const int wi = 2 * wo + dw - 1;
+          if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+            const float* px = in + ((nt * H + hi) * (long)W + wi) * 3;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) acc[(dh * 3 + dw) * 3 + ci] = fmaf(px[ci], g, acc[(dh * 3 + dw) * 3 + ci]);
+          }
+        }
+      }
+    }
+  }
+  __shared__ float sh[8][32];
+  for (int k = 0; k < 27; ++k) {
+    sh[ry][threadIdx.x & 31] = acc[k];
+    __syncthreads();
+    if (ry == 0 && c < C) {
+      double s = 0.0;
+      for (int i = 0; i < 8; ++i) s += sh[i][threadIdx.x];
+      atomicAdd(dws + (long)k * C + c, s);
+    }
+    __syncthreads();
+  }
+}
+// conv_t: kt x1x1 channelwise over T with zero pad kt/2 (model.py:170-175,187-194,205-206).
+// out[n,t,p,c] = sum_d in[n, t+d-kt/2, p, c] * wt[d',c],  d' = flip ? kt-1-d : d  (flip = backward-data)
+__global__ void __launch_bounds__(256)
+tconv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ wt, float* __restrict__ out, int T,
+                 long P, int C, int kt, int flip, long total) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long q = i / C;
+    const long pp = q % P; q /= P;
+    const int t = (int)(q % T);
+    const long n = q / T;
+    float acc = 0.f;
+    for (int d = 0; d < kt; ++d) {
+      const int ti = t + d - kt / 2;
+      if (ti < 0 || ti >= T) continue;
+      acc = fmaf(in[((n * T + ti) * P + pp) * C + c], wt[(flip ? kt - 1 - d : d) * C + c], acc);
+    }
+    out[i] = acc;
+  }
+}
+// dwt[d,c] += sum s[n, t+d-kt/2, p, c] * dy[n,t,p,c]
+__global__ void __launch_bounds__(256)
+tconv_wgrad_kernel(const float* __restrict__ s, const float* __restrict__ dy, double* __restrict__ dwt, int T,
+                   long P, int C, int kt, long rows, long rows_per_block) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  const long r0 = (long)blockIdx.y * rows_per_block;
+  long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (c < C) {
+    for (long r = r0 + ry; r < r1; r += 8) {      // r = (n*T + t)*P + p
+      const long nt = r / P, pp = r % P;
+      const int t = (int)(nt % T);
+      const float g = dy[r * C + c];
+      for (int d = 0; d < kt; ++d) {
+        const int ti = t + d - kt / 2;
+        if (ti >= 0 && ti < T) acc[d] = fmaf(s[((nt - t + ti) * P + pp) * C + c], g, acc[d]);
+      }
+    }
+  }
+  __shared__ float sh[8][32];
+  for (int d = 0; d < kt; ++d) {
+    sh[ry][threadIdx.x & 31] = acc[d];
+    __syncthreads();
+    if (ry == 0 && c < C) {
+      double sum = 0.0;
+      for (int i = 0; i < 8; ++i) sum += sh[i][threadIdx.x];
+      atomicAdd(dwt + (long)d * C + c, sum);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- elementwise pieces
+__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
+
+// out = swish(y * s[n, c])   (s == nullptr: factor 1)      model.py:311-316
+__global__ void __launch_bounds__(256)
+scale_swish_fwd_kernel(const float* __restrict__ y, const float* __restrict__ s, float* __restrict__ out,
+                       long total, int C, long rows_per_clip) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const float v = s ? y[i] * s[(i / C / rows_per_clip) * C + c] : y[i];
+    out[i] = v * sigm(v);
+  }
+}
+// dv = dout * (sig(v) * (1 + v * (1 - sig(v))));  dy = dv * s;  ds[n,c] += sum_p dv * y
+__global__ void __launch_bounds__(256)
+scale_swish_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ s,
+                       float* __restrict__ dy, double* __restrict__ ds, int C, long rows_per_clip) {
+  // grid: (ceil(C/32), row blocks of the clip, clips)
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  const long n = blockIdx.z;
+  const long r0 = n * rows_per_clip + (long)blockIdx.y * kRowsPerBlock;
+  long r1 = r0 + kRowsPerBlock;
+  if (r1 > (n + 1) * rows_per_clip) r1 = (n + 1) * rows_per_clip;
+  float acc = 0.f;
+  if (c < C) {
+    const float sc = s ? s[n * C + c] : 1.f;
+    for (long r = r0 + ry; r < r1; r += 8) {
+      const float yv = y[r * C + c], v = yv * sc, sg = sigm(v);
+      const float dv = dout[r * C + c] * (sg * (1.f + v * (1.f - sg)));
+      dy[r * C + c] = dv * sc;
+      acc = fmaf(dv, yv, acc);
+    }
+  }
+  if (ds == nullptr) return;
+  __shared__ float sh[8][32];
+  sh[ry][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    atomicAdd(ds + n * C + c, t);
+  }
+}
+// generic elementwise ops on flat arrays
+//  0: out = relu(a + b)                 (ResBlock add + ReLU, model.py:389-392)
+//  1: out = a * (b > 0)                 (ReLU backward, b = forward output)
+//  2: out = sigmoid(a)                  3: out = a * b * (1 - b)   (sigmoid backward, b = forward output)
+//  4: out = a + b                       5: out = a * b             (dropout with a precomputed mask)
+__global__ void __launch_bounds__(256)
+ew_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long n, int op) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float x = a[i], y = b ? b[i] : 0.f;
+    float r;
+    switch (op) {
+      case 0: r = fmaxf(x + y, 0.f); break;
+      case 1: r = y > 0.f ? x : 0.f; break;
+      case 2: r = sigm(x); break;
+      case 3: r = x * y * (1.f - y); break;
+      case 4: r = x + y; break;
+      default: r = x * y; break;
+    }
+    out[i] = r;
+  }
+}
+// dy[n, p, c] (+)= dm[n, c] * scale     (backward of the global average pool, scale = 1/P)
+__global__ void __launch_bounds__(256)
+pool_bwd_kernel(const float* __restrict__ dm, float* __restrict__ dy, long total, int C, long rows_per_clip,
+                float scale, int accumulate) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const float v = dm[(i / C / rows_per_clip) * C + (i % C)] * scale;
+    dy[i] = accumulate ? dy[i] + v : v;
+  }
+}
+// dst[n,t,ho*s,wo*s,c] += src[n,t,ho,wo,c]   (backward-data of the strided 'valid' shortcut conv)
+__global__ void __launch_bounds__(256)
+strided_add_kernel(const float* __restrict__ src, float* __restrict__ dst, int Ho, int Wo, int Hi, int Wi,
+                   int stride, int C, long total) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long q = i / C;
+    const int wo = (int)(q % Wo); q /= Wo;
+    const int ho = (int)(q % Ho);
+    const long nt = q / Ho;
+    dst[((nt * Hi + (long)ho * stride) * Wi + (long)wo * stride) * C + c] += src[i];
+  }
+}
+// dropout mask (keep with probability 1-rate, scaled by 1/(1-rate)); counter-based hash RNG
+__global__ void dropout_mask_kernel(float* __restrict__ mask, long n, float rate, unsigned long long seed) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.f / 16777216.f);
+  mask[i] = u >= rate ? 1.f / (1.f - rate) : 0.f;
+}
+// softmax + sparse categorical cross-entropy on the probabilities (train.py:104; Keras clips p to
+// [1e-7, 1-1e-7]) and its gradient w.r.t. the logits, scaled by `gscale` (1 / global batch).
+__global__ void __launch_bounds__(256)
+softmax_xent_kernel(const float* __restrict__ logits, const int* __restrict__ labels, float* __restrict__ loss,
+                    float* __restrict__ dlogits, int ncls, float gscale) {
+  __shared__ float sh[8];
+  const int n = blockIdx.x;
+  const float* row = logits + (long)n * ncls;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < ncls; c += blockDim.x) m = fmaxf(m, row[c]);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = sh[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, sh[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int c = threadIdx.x; c < ncls; c += blockDim.x) s += expf(row[c] - m);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i];
+  const int y = labels[n];
+  const float py = expf(row[y] - m) / s;
+  // d(-log(clip(p_y)))/dlogit_c = (p_c - [c==y]) when p_y is inside the clip range, else 0
+  const bool inside = py > 1e-7f && py < 1.f - 1e-7f;
+  for (int c = threadIdx.x; c < ncls; c += blockDim.x) {
+    const float pc = expf(row[c] - m) / s;
+    dlogits[(long)n * ncls + c] = inside ? (pc - (c == y ? 1.f : 0.f)) * gscale : 0.f;
+  }
+  if (threadIdx.x == 0) loss[n] = -logf(fminf(fmaxf(py, 1e-7f), 1.f - 1e-7f));
+}
+// SGD with Nesterov momentum and L2 (train.py:88-92; Keras: v = mu*v - lr*g; w += mu*v - lr*g),
+// g = grad + wd[i] * w  (wd = 2 * WEIGHT_DECAY on regularised kernels, 0 elsewhere; model.py:47)
+__global__ void __launch_bounds__(256)
+sgd_nesterov_kernel(float* __restrict__ w, const float* __restrict__ grad, float* __restrict__ v,
+                    const float* __restrict__ wd, long n, float lr, float mu) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float g = grad[i] + wd[i] * w[i];
+    const float vn = mu * v[i] - lr * g;
+    v[i] = vn;
+    w[i] = w[i] + mu * vn - lr * g;
+  }
+}
+
+static inline unsigned ew_blocks(long n) {
+  long b = (n + 255) / 256;
+  if (b > 148L * 32) b = 148L * 32;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace train
+}  // namespace x3d
+
+using namespace x3d;
+using namespace x3d::train;
+
+extern "C" {
+
+int x3d_colreduce(const float* a, const float* x, const float* mean, const float* rstd, const float* relu_out,
+                  int64_t M, int C, int64_t seg_rows, double* out, int mode, void* stream) {
+  X3D_REQUIRE(a && out && M > 0 && C > 0 && seg_rows > 0 && mode >= 0 && mode <= 2, X3D_ERR_INVALID_ARG, "x3d_colreduce: bad argument");
+  X3D_REQUIRE(mode != 1 || (x && mean && rstd), X3D_ERR_INVALID_ARG, "x3d_colreduce: mode 1 needs x, mean, rstd");
+  const long segs = (M + seg_rows - 1) / seg_rows;
+  const long rb = (seg_rows + kRowsPerBlock - 1) / kRowsPerBlock;
+  X3D_REQUIRE(segs <= 65535 && rb <= 65535, X3D_ERR_UNSUPPORTED, "x3d_colreduce: too many segments / row blocks");
+  dim3 grid((C + 31) / 32, (unsigned)rb, (unsigned)segs);
+  colreduce_kernel<<<grid, 256, 0, S(stream)>>>(a, x, mean, rstd, relu_out, M, C, seg_rows, out, mode);
+  return check_launch("x3d_colreduce");
+}
+
+int x3d_bn_finalize(const double* sums, int64_t M, int C, float eps, float momentum, float* mean, float* var,
+                    float* rstd, float* mov_mean, float* mov_var, void* stream) {
+  X3D_REQUIRE(sums && mean && var && rstd && M > 0 && C > 0, X3D_ERR_INVALID_ARG, "x3d_bn_finalize: bad argument");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, S(stream)>>>(sums, M, C, eps, momentum, mean, var, rstd, mov_mean, mov_var);
+  return check_launch("x3d_bn_finalize");
+}
+
+int x3d_bn_apply_fwd(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                     float* y, int64_t M, int C, int relu, void* stream) {
+  X3D_REQUIRE(x && mean && rstd && gamma && beta && y && M > 0 && C > 0, X3D_ERR_INVALID_ARG, "x3d_bn_apply_fwd: bad argument");
+  bn_apply_kernel<<<ew_blocks(M * C), 256, 0, S(stream)>>>(x, mean, rstd, gamma, beta, y, M * C, C, relu);
+  return check_launch("x3d_bn_apply_fwd");
+}
+
+int x3d_bn_bwd_apply(const float* dy, const float* x, const float* relu_out, const float* mean, const float* rstd,
+                     const float* gamma, const double* sums, float* dx, int64_t M, int C, void* stream) {
+  X3D_REQUIRE(dy && x && mean && rstd && gamma && sums && dx && M > 0 && C > 0, X3D_ERR_INVALID_ARG, "x3d_bn_bwd_apply: bad argument");
+  bn_bwd_apply_kernel<<<ew_blocks(M * C), 256, 0, S(stream)>>>(dy, x, relu_out, mean, rstd, gamma, sums, dx, M * C, C, M);
+  return check_launch("x3d_bn_bwd_apply");
+}
+
+int x3d_d2f(const double* in, float* out, int64_t n, float scale, void* stream) {
+  X3D_REQUIRE(in && out && n > 0, X3D_ERR_INVALID_ARG, "x3d_d2f: bad argument");
+  d2f_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(in, out, n, scale);
+  return check_launch("x3d_d2f");
+}
+
+int x3d_pw_wgrad(const float* A, const float* dD, double* dW, int64_t M, int K, int N, int lda, int ldd, int gather,
+                 int Ho, int Wo, int Hi, int Wi, int stride, void* stream) {
+  X3D_REQUIRE(A && dD && dW && M > 0 && K > 0 && N > 0, X3D_ERR_INVALID_ARG, "x3d_pw_wgrad: bad argument");
+  long rpb = 2048;
+  long zb = (M + rpb - 1) / rpb;
+  if (zb > 4096) { rpb = (M + 4095) / 4096; rpb = (rpb + 31) / 32 * 32; zb = (M + rpb - 1) / rpb; }
+  dim3 grid((K + 31) / 32, (N + 31) / 32, (unsigned)zb);
+  pw_wgrad_kernel<<<grid, 256, 0, S(stream)>>>(A, dD, dW, M, K, N, lda, ldd, rpb, gather, Ho, Wo, Hi, Wi, stride);
+  return check_launch("x3d_pw_wgrad");
+}
+
+int x3d_dw_dgrad(const float* dy, const float* w, float* dx, int N, int T, int H, int W, int C, int stride, int pad_h,
+                 int pad_w, void* stream) {
+  X3D_REQUIRE(dy && w && dx && N > 0 && T > 0 && H > 0 && W > 0 && C > 0 && (stride == 1 || stride == 2), X3D_ERR_INVALID_ARG, "x3d_dw_dgrad: bad argument");
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  const long total = (long)N * T * H * W * C;
+  dw_dgrad_kernel<<<ew_blocks(total), 256, 0, S(stream)>>>(dy, w, dx, T, H, W, Ho, Wo, C, stride, pad_h, pad_w, total);
+  return check_launch("x3d_dw_dgrad");
+}
+
+int x3d_dw_wgrad(const float* x, const float* dy, double* dwt, int N, int T, int H, int W, int C, int stride, int pad_h,
+                 int pad_w, void* stream) {
+  X3D_REQUIRE(x && dy && dwt && N > 0 && T > 0 && H > 0 && W > 0 && C > 0 && (stride == 1 || stride == 2), X3D_ERR_INVALID_ARG, "x3d_dw_wgrad: bad argument");
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  const long opix = (long)N * T * Ho * Wo;
+  long ppb = 1024;
+  long yb = (opix + ppb - 1) / ppb;
+  if (yb > 65535) { ppb = (opix + 65534) / 65535; yb = (opix + ppb - 1) / ppb; }
+  dim3 grid((C + 31) / 32, (unsigned)yb);
+  dw_wgrad_kernel<<<grid, 256, 0, S(stream)>>>(x, dy, dwt, T, H, W, Ho, Wo, C, stride, pad_h, pad_w, opix, ppb);
+  return check_launch("x3d_dw_wgrad");
+}
+
+int x3d_stem_convs_fwd(const float* in, const float* ws, float* out, int N, int T, int H, int W, int C, void* stream) {
+  X3D_REQUIRE(in && ws && out && N > 0 && T > 0 && H > 0 && W > 0 && C > 0, X3D_ERR_INVALID_ARG, "x3d_stem_convs_fwd: bad argument");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long total = (long)N * T * Ho * Wo * C;
+  stem_convs_fwd_kernel<<<ew_blocks(total), 256, 0, S(stream)>>>(in, ws, out, H, W, Ho, Wo, C, total);
+  return check_launch("x3d_stem_convs_fwd");
+}
+
+int x3d_stem_convs_wgrad(const float* in, const float* ds, double* dws, int N, int T, int H, int W, int C, void* stream) {
+  X3D_REQUIRE(in && ds && dws && N > 0 && T > 0 && H > 0 && W > 0 && C > 0, X3D_ERR_INVALID_ARG, "x3d_stem_convs_wgrad: bad argument");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long opix = (long)N * T * Ho * Wo;
+  long ppb = 1024;
+  long yb = (opix + ppb - 1) / ppb;
+  if (yb > 65535) { ppb = (opix + 65534) / 65535; yb = (opix + ppb - 1) / ppb; }
+  dim3 grid((C + 31) / 32, (unsigned)yb);
+  stem_convs_wgrad_kernel<<<grid, 256, 0, S(stream)>>>(in, ds, dws, H, W, Ho, Wo, C, opix, ppb);
+  return check_launch("x3d_stem_convs_wgrad");
+}
+
+int x3d_tconv_fwd(const float* in, const float* wt, float* out, int N, int T, int64_t P, int C, int kt, int flip, void* stream) {
+  X3D_REQUIRE(in && wt && out && N > 0 && T > 0 && P > 0 && C > 0 && kt > 0 && kt <= 8 && (kt & 1), X3D_ERR_INVALID_ARG, "x3d_tconv_fwd: bad argument");
+  const long total = (long)N * T * P * C;
+  tconv_fwd_kernel<<<ew_blocks(total), 256, 0, S(stream)>>>(in, wt, out, T, P, C, kt, flip, total);
+  return check_launch("x3d_tconv_fwd");
+}
+
+int x3d_tconv_wgrad(const float* s, const float* dy, double* dwt, int N, int T, int64_t P, int C, int kt, void* stream) {
+  X3D_REQUIRE(s && dy && dwt && N > 0 && T > 0 && P > 0 && C > 0 && kt > 0 && kt <= 8, X3D_ERR_INVALID_ARG, "x3d_tconv_wgrad: bad argument");
+  const long rows = (long)N * T * P;
+  long rpb = 1024;
+  long yb = (rows + rpb - 1) / rpb;
+  if (yb > 65535) { rpb = (rows + 65534) / 65535; yb = (rows + rpb - 1) / rpb; }
+  dim3 grid((C + 31) / 32, (unsigned)yb);
+  tconv_wgrad_kernel<<<grid, 256, 0, S(stream)>>>(s, dy, dwt, T, P, C, kt, rows, rpb);
+  return check_launch("x3d_tconv_wgrad");
+}
+
+int x3d_scale_swish_fwd(const float* y, const float* s, float* out, int64_t M, int C, int64_t rows_per_clip, void* stream) {
+  X3D_REQUIRE(y && out && M > 0 && C > 0 && rows_per_clip > 0, X3D_ERR_INVALID_ARG, "x3d_scale_swish_fwd: bad argument");
+  scale_swish_fwd_kernel<<<ew_blocks(M * C), 256, 0, S(stream)>>>(y, s, out, M * C, C, rows_per_clip);
+  return check_launch("x3d_scale_swish_fwd");
+}
+
+int x3d_scale_swish_bwd(const float* dout, const float* y, const float* s, float* dy, double* ds, int64_t M, int C,
+                        int64_t rows_per_clip, void* stream) {
+  X3D_REQUIRE(dout && y && dy && M > 0 && C > 0 && rows_per_clip > 0 && M % rows_per_clip == 0, X3D_ERR_INVALID_ARG, "x3d_scale_swish_bwd: bad argument");
+  X3D_REQUIRE((s == nullptr) == (ds == nullptr), X3D_ERR_INVALID_ARG, "x3d_scale_swish_bwd: s and ds go together");
+  const long clips = M / rows_per_clip, rb = (rows_per_clip + kRowsPerBlock - 1) / kRowsPerBlock;
+  X3D_REQUIRE(clips <= 65535 && rb <= 65535, X3D_ERR_UNSUPPORTED, "x3d_scale_swish_bwd: too many clips / row blocks");
+  dim3 grid((C + 31) / 32, (unsigned)rb, (unsigned)clips);
+  scale_swish_bwd_kernel<<<grid, 256, 0, S(stream)>>>(dout, y, s, dy, ds, C, rows_per_clip);
+  return check_launch("x3d_scale_swish_bwd");
+}
+
+int x3d_ew(const float* a, const float* b, float* out, int64_t n, int op, void* stream) {
+  X3D_REQUIRE(a && out && n > 0 && op >= 0 && op <= 5, X3D_ERR_INVALID_ARG, "x3d_ew: bad argument");
+  X3D_REQUIRE(b || op == 2, X3D_ERR_INVALID_ARG, "x3d_ew: op %d needs two inputs", op);
+  ew_kernel<<<ew_blocks(n), 256, 0, S(stream)>>>(a, b, out, n, op);
+  return check_launch("x3d_ew");
+}
+
+int x3d_pool_bwd(const float* dm, float* dy, int64_t M, int C, int64_t rows_per_clip, float scale, int accumulate, void* stream) {
+  X3D_REQUIRE(dm && dy && M > 0 && C > 0 && rows_per_clip > 0, X3D_ERR_INVALID_ARG, "x3d_pool_bwd: bad argument");
+  pool_bwd_kernel<<<ew_blocks(M * C), 256, 0, S(stream)>>>(dm, dy, M * C, C, rows_per_clip, scale, accumulate);
+  return check_launch("x3d_pool_bwd");
+}
+
+int x3d_strided_add(const float* src, float* dst, int NT, int Ho, int Wo, int Hi, int Wi, int stride, int C, void* stream) {
+  X3D_REQUIRE(src && dst && NT > 0 && Ho > 0 && Wo > 0 && C > 0 && stride >= 1, X3D_ERR_INVALID_ARG, "x3d_strided_add: bad argument");
+  const long total = (long)NT * Ho * Wo * C;
+  strided_add_kernel<<<ew_blocks(total), 256, 0, S(stream)>>>(src, dst, Ho, Wo, Hi, Wi, stride, C, total);
+  return check_launch("x3d_strided_add");
+}
+
+int x3d_dropout_mask(float* mask, int64_t n, float rate, uint64_t seed, void* stream) {
+  X3D_REQUIRE(mask && n > 0 && rate >= 0.f && rate < 1.f, X3D_ERR_INVALID_ARG, "x3d_dropout_mask: bad argument");
+  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(mask, n, rate, seed);
+  return check_launch("x3d_dropout_mask");
+}
+
+int x3d_softmax_xent(const float* logits, const int32_t* labels, float* loss, float* dlogits, int N, int ncls,
+                     float gscale, void* stream) {
+  X3D_REQUIRE(logits && labels && loss && dlogits && N > 0 && ncls > 0, X3D_ERR_INVALID_ARG, "x3d_softmax_xent: bad argument");
+  softmax_xent_kernel<<<N, 256, 0, S(stream)>>>(logits, labels, loss, dlogits, ncls, gscale);
+  return check_launch("x3d_softmax_xent");
+}
+
+int x3d_sgd_nesterov_step(float* w, const float* grad, float* v, const float* wd, int64_t n, float lr, float momentum,
+                          void* stream) {
+  X3D_REQUIRE(w && grad && v && wd && n > 0, X3D_ERR_INVALID_ARG, "x3d_sgd_nesterov_step: bad argument");
+  sgd_nesterov_kernel<<<ew_blocks(n), 256, 0, S(stream)>>>(w, grad, v, wd, n, lr, momentum);
+  return check_launch("x3d_sgd_nesterov_step");
+}
+
+}  // extern "C"
