@@ -164,6 +164,25 @@ int x3d_expand_dw_fwd(const void* x, const void* wa, const float* bias_a, const 
                       int W, int Cin, int C, int Kpad, int Npad, int stride, int pad_h, int pad_w,
                       void* stream);
 
+/* ==== Either side of the forward path ==================================
+ * Input stage: utils.normalize, utils.py:42-72 (called from dataloader.py on decoded frames):
+ *   out[p,c] = ((in[p,c] / norm_value) - mean[c]) / std[c]   in fp32, the reference's operation order.
+ * `mean` / `std` are HOST pointers to 3 floats (cfg.DATA.MEAN / cfg.DATA.STD), read at call time.
+ * in [pixels,3] uint8 (4-byte aligned) -> out [pixels,3] fp32 or bf16 (16-byte aligned). */
+int x3d_normalize_u8(const uint8_t* in, void* out, int64_t pixels, const float* mean,
+                     const float* std, float norm_value, int dtype, void* stream);
+/* x3d_stem_tc_fwd with the input stage fused into its loader: uint8 NDHWC clips in, bf16
+ * activations out (same result as x3d_normalize_u8(bf16) followed by x3d_stem_tc_fwd). */
+int x3d_stem_tc_u8_fwd(const uint8_t* in, const float* mean, const float* std, float norm_value,
+                       const void* wc, const float* bias, void* out, int N, int T, int H, int W,
+                       int C, int kt, void* stream);
+/* Evaluation metrics, eval.py:62-70 (model.compile(loss=SparseCategoricalCrossentropy, metrics=
+ * [SparseCategoricalAccuracy, SparseTopKCategoricalAccuracy(k=5)])):  probs [V,ncls] fp32, labels
+ * [V] int32;  acc[0] += sum of losses, acc[1] += top-1 hits, acc[2] += top-k hits, acc[3] += V
+ * (caller-zeroed fp64[4] on the device, so shards and batches accumulate). */
+int x3d_eval_metrics(const float* probs, const int32_t* labels, double* acc, int V, int ncls,
+                     int k, void* stream);
+
 /* ==== Training step (BASELINE configs[4]; train.py:85-152 -> Keras train_step) ================
  * fp32, channels-last, activations viewed as [M, C] matrices (M = N*T*H*W).  Reductions accumulate
  * into caller-zeroed fp64 buffers.  The forward convolutions of the training step are the entry

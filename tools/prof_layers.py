@@ -12,6 +12,7 @@ ap.add_argument("--size", type=int, default=224)
 ap.add_argument("--clips", type=int, default=8)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--T", type=int, default=16)
+ap.add_argument("--se", type=int, default=1)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 N, T, S0 = a.clips, a.T, a.size // 2
@@ -36,8 +37,8 @@ for si, (Hin, cin, inner, cout) in enumerate(stages):
         if a.what in ("dw", "all"):
             x = rnd(N, T, H, H, ci); w = rnd(27, ci, dtype=torch.float32); b = rnd(ci, dtype=torch.float32)
             _, ph, _ = same_pad(H, 3, stride)
-            for se in (True,):
-                timeit(f"dw s{si+2} {H}x{H}x{ci} stride{stride}", lambda: ops.dw_fwd(x, w, b, stride, ph, ph, se),
+            for se in (bool(a.se),):
+                timeit(f"dw s{si+2} {H}x{H}x{ci} stride{stride} se{int(se)}", lambda: ops.dw_fwd(x, w, b, stride, ph, ph, se),
                        (x.numel() + N * T * Ho * Ho * ci) * 2)
         if a.what in ("ab", "all"):
             cin_s = pad8(cin if stride == 2 else cout)

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libx3d_b200.so")
-SOURCES = ["host_util.cu", "x3d_simt.cu", "x3d_pw_tc.cu", "x3d_dw_tma.cu", "x3d_stem_tc.cu", "x3d_ab_fused.cu", "x3d_train.cu"]
+SOURCES = ["host_util.cu", "x3d_simt.cu", "x3d_pw_tc.cu", "x3d_dw_tma.cu", "x3d_stem_tc.cu", "x3d_ab_fused.cu", "x3d_train.cu", "x3d_io.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
               "--expt-relaxed-constexpr"]
@@ -37,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "x3d_b200.h"))
-    objs = []
+    objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
@@ -46,7 +46,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd))
-            subprocess.run(cmd, check=True)
+            jobs.append(subprocess.Popen(cmd))
+    failed = [j.args for j in jobs if j.wait() != 0]
+    if failed:
+        raise subprocess.CalledProcessError(1, failed[0])
     if force or _stale(LIB_PATH, objs):
         cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-cudart", "static"]
         if verbose:

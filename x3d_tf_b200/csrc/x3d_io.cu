@@ -1,0 +1,125 @@
+// The two steps either side of the forward path that run on the device:
+//   * input stage  -- utils.normalize (reference utils.py:42-72) on decoded uint8 frames;
+//   * eval metrics -- the loss and metrics eval.py:62-70 compiles into the model
+//     (SparseCategoricalCrossentropy on probabilities, SparseCategoricalAccuracy,
+//     SparseTopKCategoricalAccuracy(k)).
+#include "common.cuh"
+
+namespace x3d {
+namespace io {
+
+struct Norm {
+  float mean[3], std[3], nv;
+};
+
+// Same fp32 operation order as the reference: x / norm_value, then (x - mean) / std.
+__device__ __forceinline__ float normalize1(float u, float nv, float mean, float std) {
+  return __fdiv_rn(__fsub_rn(__fdiv_rn(u, nv), mean), std);
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256)
+normalize_u8_kernel(const uint8_t* __restrict__ in, TO* __restrict__ out, int64_t pixels, const Norm nrm) {
+  // one thread = 4 pixels = 12 bytes in (three 32-bit loads), 12 values out
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t groups = pixels / 4;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(in + g * 12);
+    uint32_t w[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
+    float v[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const float u = static_cast<float>((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+      v[i] = normalize1(u, nrm.nv, nrm.mean[i % 3], nrm.std[i % 3]);
+    }
+    TO* dst = out + g * 12;
+#pragma unroll
+    for (int i = 0; i < 12; i += 4) {
+      const float q[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
+      st4(dst + i, q);
+    }
+  }
+  // tail (pixels % 4) by the first threads of block 0
+  if (blockIdx.x == 0) {
+    const int64_t done = groups * 4;
+    for (int64_t e = done * 3 + threadIdx.x; e < pixels * 3; e += blockDim.x) {
+      const float r = normalize1(static_cast<float>(in[e]), nrm.nv, nrm.mean[e % 3], nrm.std[e % 3]);
+      if (sizeof(TO) == 4) reinterpret_cast<float*>(out)[e] = r;
+      else reinterpret_cast<bf16*>(out)[e] = __float2bfloat16_rn(r);
+    }
+  }
+}
+
+// One warp per video.  Keras semantics (TF 2.4 backend.sparse_categorical_crossentropy with
+// from_logits=False on a tensor that is not a Softmax op output -- eval-mode X3D.call returns a
+// mean over views): p = clip(p, 1e-7, 1 - 1e-7); loss = -(log p[label] - log sum_j p[j]).
+// top-1: argmax (first maximal index) == label.  top-k: tf.math.in_top_k, i.e. fewer than k
+// classes have a strictly larger probability.
+__global__ void __launch_bounds__(128)
+eval_metrics_kernel(const float* __restrict__ probs, const int32_t* __restrict__ labels,
+                    double* __restrict__ acc, int V, int ncls, int k) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= V) return;
+  const float* p = probs + static_cast<int64_t>(warp) * ncls;
+  const int label = labels[warp];
+  if (label < 0 || label >= ncls) return;                   // counted as a miss with zero loss
+  const float pl = p[label];
+  int greater = 0, before = 0;
+  float sum = 0.f;
+  for (int j = lane; j < ncls; j += 32) {
+    const float v = p[j];
+    greater += v > pl;
+    before += (v == pl && j < label);
+    sum += fminf(fmaxf(v, 1e-7f), 1.f - 1e-7f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    greater += __shfl_xor_sync(0xffffffffu, greater, o);
+    before += __shfl_xor_sync(0xffffffffu, before, o);
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  }
+  if (lane == 0) {
+    const float plc = fminf(fmaxf(pl, 1e-7f), 1.f - 1e-7f);
+    atomicAdd(acc + 0, static_cast<double>(logf(sum) - logf(plc)));
+    atomicAdd(acc + 1, (greater == 0 && before == 0) ? 1.0 : 0.0);
+    atomicAdd(acc + 2, greater < k ? 1.0 : 0.0);
+    atomicAdd(acc + 3, 1.0);
+  }
+}
+
+}  // namespace io
+}  // namespace x3d
+
+using namespace x3d;
+
+extern "C" int x3d_normalize_u8(const uint8_t* in, void* out, int64_t pixels, const float* mean,
+                                const float* std, float norm_value, int dtype, void* stream) {
+  X3D_REQUIRE(in && out && mean && std, X3D_ERR_INVALID_ARG, "x3d_normalize_u8: null pointer");
+  X3D_REQUIRE(pixels > 0, X3D_ERR_INVALID_ARG, "x3d_normalize_u8: pixels=%lld", (long long)pixels);
+  X3D_REQUIRE(dtype == X3D_F32 || dtype == X3D_BF16, X3D_ERR_INVALID_ARG, "x3d_normalize_u8: dtype %d", dtype);
+  X3D_REQUIRE(norm_value != 0.f && std[0] != 0.f && std[1] != 0.f && std[2] != 0.f, X3D_ERR_INVALID_ARG,
+              "x3d_normalize_u8: zero divisor");
+  X3D_REQUIRE((reinterpret_cast<uintptr_t>(in) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              X3D_ERR_INVALID_ARG, "x3d_normalize_u8: in must be 4-byte, out 16-byte aligned");
+  io::Norm nrm;
+  for (int i = 0; i < 3; ++i) { nrm.mean[i] = mean[i]; nrm.std[i] = std[i]; }
+  nrm.nv = norm_value;
+  const int64_t groups = (pixels + 3) / 4;
+  int64_t blocks = (groups + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == X3D_F32)
+    io::normalize_u8_kernel<float><<<(int)blocks, 256, 0, st>>>(in, static_cast<float*>(out), pixels, nrm);
+  else
+    io::normalize_u8_kernel<bf16><<<(int)blocks, 256, 0, st>>>(in, static_cast<bf16*>(out), pixels, nrm);
+  return check_launch("x3d_normalize_u8");
+}
+
+extern "C" int x3d_eval_metrics(const float* probs, const int32_t* labels, double* acc, int V, int ncls,
+                                int k, void* stream) {
+  X3D_REQUIRE(probs && labels && acc, X3D_ERR_INVALID_ARG, "x3d_eval_metrics: null pointer");
+  X3D_REQUIRE(V > 0 && ncls > 0 && k > 0, X3D_ERR_INVALID_ARG, "x3d_eval_metrics: V=%d ncls=%d k=%d", V, ncls, k);
+  const int blocks = (V + 3) / 4;
+  io::eval_metrics_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(probs, labels, acc, V, ncls, k);
+  return check_launch("x3d_eval_metrics");
+}

@@ -74,20 +74,31 @@ __device__ __forceinline__ uint32_t to_bf16_bits(float x) {
   __nv_bfloat16 h = __float2bfloat16_rn(x);
   return static_cast<uint32_t>(*reinterpret_cast<unsigned short*>(&h));
 }
-__device__ __forceinline__ uint32_t load_bf16_bits(const float* p) { return to_bf16_bits(__ldg(p)); }
-__device__ __forceinline__ uint32_t load_bf16_bits(const bf16* p) {
+// `lut` is only used by the uint8 input stage: [3][256] bf16 bits of ((u/nv) - mean[c]) / std[c]
+__device__ __forceinline__ uint32_t load_bf16_bits(const float* p, const unsigned short*, int) {
+  return to_bf16_bits(__ldg(p));
+}
+__device__ __forceinline__ uint32_t load_bf16_bits(const bf16* p, const unsigned short*, int) {
   return static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(p)));
 }
+__device__ __forceinline__ uint32_t load_bf16_bits(const uint8_t* p, const unsigned short* lut, int ch) {
+  return static_cast<uint32_t>(lut[ch * 256 + __ldg(p)]);
+}
+
+// utils.normalize (reference utils.py:42-72): x / norm_value, then (x - mean) / std, fp32.
+struct InputNorm {
+  float mean[3], std[3], norm_value;
+};
 
 template <typename TI>
 __global__ void __launch_bounds__(kThreads)
 stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const float* __restrict__ bias,
-               bf16* __restrict__ out, int T, int H, int W, int Ho, int Wo, int C) {
+               bf16* __restrict__ out, int T, int H, int W, int Ho, int Wo, int C, const InputNorm nrm) {
   extern __shared__ __align__(128) uint8_t stem_smem_raw[];
   const uint32_t raw_s = smem_u32(stem_smem_raw);
   const uint32_t smem_s = (raw_s + 127u) & ~127u;
   uint8_t* smem = stem_smem_raw + (smem_s - raw_s);
-  // layout: [A ring kRing x 8 KB][W kKT x 2 KB][bias 32 f32][barriers][tmem slot]
+  // layout: [A ring kRing x 8 KB][W kKT x 2 KB][bias 32 f32][barriers][tmem slot][u8 LUT 3x256 u16]
   const uint32_t a_s = smem_s;
   const uint32_t w_s = a_s + kRing * kABytes;
   float* s_bias = reinterpret_cast<float*>(smem + kRing * kABytes + kKT * kWBytes);
@@ -95,6 +106,7 @@ stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const fl
   uint64_t* t_full = built + kRing;                               // [2] accumulator ready
   uint64_t* t_empty = t_full + 2;                                 // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  unsigned short* s_lut = reinterpret_cast<unsigned short*>(tmem_slot + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int n = blockIdx.z;
@@ -106,6 +118,16 @@ stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const fl
   for (int i = tid; i < kKT * kWBytes / 16; i += kThreads)
     reinterpret_cast<uint4*>(smem + kRing * kABytes)[i] = __ldg(wc + i);
   if (tid < 32) s_bias[tid] = tid < C ? bias[tid] : 0.f;
+  if (sizeof(TI) == 1) {
+    // input stage fused into the loader: the 256 possible pixel values of each channel, normalised
+    // in the reference's fp32 operation order and rounded to bf16 once
+    for (int i = tid; i < 768; i += kThreads) {
+      const int ch = i >> 8;
+      const float v = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(i & 255), nrm.norm_value), nrm.mean[ch]),
+                                nrm.std[ch]);
+      s_lut[i] = static_cast<unsigned short>(to_bf16_bits(v));
+    }
+  }
   if (tid == 0) {
     for (int i = 0; i < kRing; ++i) mbar_init(&built[i], kPix);
     for (int i = 0; i < 2; ++i) {
@@ -158,7 +180,7 @@ stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const fl
 #pragma unroll
         for (int e = 0; e < 9; ++e) {
           const bool ok = rv[dh] && cv[e / 3];
-          vals[dh * 9 + e] = ok ? load_bf16_bits(src + dh * row_elems + e) : 0u;
+          vals[dh * 9 + e] = ok ? load_bf16_bits(src + dh * row_elems + e, s_lut, e % 3) : 0u;
         }
       vals[27] = 0u;
     };
@@ -251,15 +273,36 @@ stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const fl
   }
 }
 
-constexpr size_t kSmemBytes = 128 + kRing * kABytes + kKT * kWBytes + 128 + 128 + 16;
+constexpr size_t kSmemBytes = 128 + kRing * kABytes + kKT * kWBytes + 128 + 128 + 16 + 768 * 2;
 
 }  // namespace stemtc
 }  // namespace x3d
 
 using namespace x3d;
 
-extern "C" int x3d_stem_tc_fwd(const void* in, int in_dtype, const void* wc, const float* bias,
-                               void* out, int N, int T, int H, int W, int C, int kt, void* stream) {
+template <typename TI>
+static int stem_tc_launch(const void* in, const void* wc, const float* bias, void* out, int N, int T, int H,
+                          int W, int C, const stemtc::InputNorm& nrm, cudaStream_t st) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  dim3 grid((Wo + stemtc::kTW - 1) / stemtc::kTW, (Ho + stemtc::kTH - 1) / stemtc::kTH, N);
+  X3D_REQUIRE(grid.y <= 65535, X3D_ERR_UNSUPPORTED, "x3d_stem_tc_fwd: image too tall");
+  static bool configured = false;                   // one flag per input type (template instance)
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(stemtc::stem_tc_kernel<TI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)stemtc::kSmemBytes);
+    X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_stem_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
+    cudaFuncSetAttribute(stemtc::stem_tc_kernel<TI>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  stemtc::stem_tc_kernel<TI><<<grid, stemtc::kThreads, stemtc::kSmemBytes, st>>>(
+      static_cast<const TI*>(in), static_cast<const uint4*>(wc), bias, static_cast<bf16*>(out), T, H, W, Ho, Wo,
+      C, nrm);
+  return check_launch("x3d_stem_tc_fwd");
+}
+
+static int stem_tc_check(const void* in, const void* wc, const float* bias, void* out, int N, int T, int H,
+                         int W, int C, int kt) {
   X3D_REQUIRE(in && wc && bias && out, X3D_ERR_INVALID_ARG, "x3d_stem_tc_fwd: null pointer");
   X3D_REQUIRE(kt == stemtc::kKT, X3D_ERR_UNSUPPORTED, "x3d_stem_tc_fwd: temporal filter %d (only 5)", kt);
   X3D_REQUIRE(C > 0 && C % 8 == 0 && C <= stemtc::kN, X3D_ERR_UNSUPPORTED, "x3d_stem_tc_fwd: C=%d (multiple of 8, <= 32)", C);
@@ -268,32 +311,30 @@ extern "C" int x3d_stem_tc_fwd(const void* in, int in_dtype, const void* wc, con
   X3D_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(wc) & 15) == 0,
               X3D_ERR_INVALID_ARG, "x3d_stem_tc_fwd: out / wc must be 16-byte aligned");
   X3D_REQUIRE(device_sm_count() > 0 && device_is_sm100(), X3D_ERR_NO_DEVICE, "x3d_stem_tc_fwd: needs an sm_100 device");
-  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  dim3 grid((Wo + stemtc::kTW - 1) / stemtc::kTW, (Ho + stemtc::kTH - 1) / stemtc::kTH, N);
-  X3D_REQUIRE(grid.y <= 65535, X3D_ERR_UNSUPPORTED, "x3d_stem_tc_fwd: image too tall");
+  return X3D_OK;
+}
+
+extern "C" int x3d_stem_tc_fwd(const void* in, int in_dtype, const void* wc, const float* bias,
+                               void* out, int N, int T, int H, int W, int C, int kt, void* stream) {
+  const int rc = stem_tc_check(in, wc, bias, out, N, T, H, W, C, kt);
+  if (rc != X3D_OK) return rc;
+  const stemtc::InputNorm none{};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool configured[2] = {false, false};
-  cudaError_t e = cudaSuccess;
-  if (in_dtype == X3D_BF16) {
-    if (!configured[0]) {
-      e = cudaFuncSetAttribute(stemtc::stem_tc_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stemtc::kSmemBytes);
-      cudaFuncSetAttribute(stemtc::stem_tc_kernel<bf16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      configured[0] = e == cudaSuccess;
-    }
-    X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_stem_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
-    stemtc::stem_tc_kernel<bf16><<<grid, stemtc::kThreads, stemtc::kSmemBytes, st>>>(
-        static_cast<const bf16*>(in), static_cast<const uint4*>(wc), bias, static_cast<bf16*>(out), T, H, W, Ho, Wo, C);
-  } else if (in_dtype == X3D_F32) {
-    if (!configured[1]) {
-      e = cudaFuncSetAttribute(stemtc::stem_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stemtc::kSmemBytes);
-      cudaFuncSetAttribute(stemtc::stem_tc_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      configured[1] = e == cudaSuccess;
-    }
-    X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_stem_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
-    stemtc::stem_tc_kernel<float><<<grid, stemtc::kThreads, stemtc::kSmemBytes, st>>>(
-        static_cast<const float*>(in), static_cast<const uint4*>(wc), bias, static_cast<bf16*>(out), T, H, W, Ho, Wo, C);
-  } else {
-    X3D_REQUIRE(false, X3D_ERR_INVALID_ARG, "x3d_stem_tc_fwd: in_dtype %d", in_dtype);
-  }
-  return check_launch("x3d_stem_tc_fwd");
+  if (in_dtype == X3D_BF16) return stem_tc_launch<bf16>(in, wc, bias, out, N, T, H, W, C, none, st);
+  if (in_dtype == X3D_F32) return stem_tc_launch<float>(in, wc, bias, out, N, T, H, W, C, none, st);
+  X3D_REQUIRE(false, X3D_ERR_INVALID_ARG, "x3d_stem_tc_fwd: in_dtype %d", in_dtype);
+}
+
+extern "C" int x3d_stem_tc_u8_fwd(const uint8_t* in, const float* mean, const float* std, float norm_value,
+                                  const void* wc, const float* bias, void* out, int N, int T, int H, int W,
+                                  int C, int kt, void* stream) {
+  const int rc = stem_tc_check(in, wc, bias, out, N, T, H, W, C, kt);
+  if (rc != X3D_OK) return rc;
+  X3D_REQUIRE(mean && std, X3D_ERR_INVALID_ARG, "x3d_stem_tc_u8_fwd: null mean/std");
+  X3D_REQUIRE(norm_value != 0.f && std[0] != 0.f && std[1] != 0.f && std[2] != 0.f, X3D_ERR_INVALID_ARG,
+              "x3d_stem_tc_u8_fwd: zero divisor");
+  stemtc::InputNorm nrm;
+  for (int i = 0; i < 3; ++i) { nrm.mean[i] = mean[i]; nrm.std[i] = std[i]; }
+  nrm.norm_value = norm_value;
+  return stem_tc_launch<uint8_t>(in, wc, bias, out, N, T, H, W, C, nrm, static_cast<cudaStream_t>(stream));
 }

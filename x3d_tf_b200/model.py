@@ -169,7 +169,7 @@ def _as_device_clip(x, device) -> torch.Tensor:
         raise ValueError(f"expected a 5-D NDHWC tensor, got shape {tuple(x.shape)}")
     if x.dtype == torch.float16 or x.dtype == torch.float64:
         x = x.to(torch.float32)
-    if x.dtype not in (torch.float32, torch.bfloat16):
+    if x.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
         raise TypeError(f"unsupported input dtype {x.dtype}")
     if not x.is_cuda:
         if device is None:
@@ -250,6 +250,9 @@ class X3D_Stem(Layer):
         self._add_conv("conv_t/kernel", (temp_filter_size, 1, 1, 1, out_channels),
                        groups=out_channels)
         self._add_bn("bn", out_channels)
+        # uint8 clips are normalised on the device the way dataloader.py does on the host
+        # (utils.normalize, utils.py:42-72); X3D sets this from cfg.DATA.MEAN / STD
+        self.input_norm: Optional[Tuple[tuple, tuple]] = None
 
     def _prep(self, device):
         key = (str(device),)
@@ -275,14 +278,23 @@ class X3D_Stem(Layer):
     def _forward(self, x: torch.Tensor, out_dtype) -> torch.Tensor:
         d = self._prep(x.device)
         ops.Profiler.tag = "stem"
-        if out_dtype == torch.bfloat16 and "wc" in d and Options.stem == "tc":
+        tc = out_dtype == torch.bfloat16 and "wc" in d and Options.stem == "tc"
+        if x.dtype == torch.uint8:
+            if self.input_norm is None:
+                raise ValueError("uint8 clips need input_norm = (mean, std) (cfg.DATA.MEAN / cfg.DATA.STD)")
+            mean, std = self.input_norm
+            if tc:
+                return ops.stem_tc_u8_fwd(x, mean, std, d["wc"], d["bias"])
+            x = ops.normalize_u8(x, mean, std, out_dtype)
+        if tc:
             return ops.stem_tc_fwd(x, d["wc"], d["bias"])
         return ops.stem_fwd(x, d["ws"], d["wt"], d["bias"], out_dtype)
 
     def call(self, input, training: bool = False):
         self._no_training(training)
         x = _as_device_clip(input, None)
-        return self._forward(x, x.dtype)[..., :self.out_channels]
+        out_dtype = torch.float32 if x.dtype == torch.uint8 else x.dtype
+        return self._forward(x, out_dtype)[..., :self.out_channels]
 
 
 class AdaptiveAvgPool3D(Layer):
@@ -495,6 +507,21 @@ class ResStage(Layer):
         return y[..., :self.out_channels]
 
 
+def finalize_metrics(acc: torch.Tensor, group=None, k: int = 5, return_dict: bool = True):
+    """[sum loss, top-1 hits, top-k hits, videos] (per rank) -> Keras-style results.  Sums over the
+    ranks of `group` first when torch.distributed is initialised (sum all-reduce of 32 bytes)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        backend = dist.get_backend(group)
+        buf = acc if (backend == "nccl") == acc.is_cuda else (acc.cuda() if backend == "nccl" else acc.cpu())
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        acc = buf
+    a = [float(v) for v in acc.detach().cpu().tolist()]
+    count = max(a[3], 1.0)
+    res = {"loss": a[0] / count, "acc": a[1] / count, f"top_{k}_acc": a[2] / count, "videos": int(a[3])}
+    return res if return_dict else [res["loss"], res["acc"], res[f"top_{k}_acc"]]
+
+
 def reset_block_counters() -> None:
     """Back to the fresh-process state of the reference's class counters (model.py:326,401)."""
     ResBlock._block_index = 0
@@ -568,6 +595,8 @@ class X3D(Layer):
             regularizer=None, bn_cfg=cfg.NETWORK.BN, out_channels=self._conv1_dim,
             temp_filter_size=cfg.NETWORK.C1_TEMP_FILTER,
             in_channels=cfg.DATA.NUM_INPUT_CHANNELS))
+        if cfg.DATA.NUM_INPUT_CHANNELS == 3:
+            self.conv1.input_norm = (tuple(cfg.DATA.MEAN), tuple(cfg.DATA.STD))
         self.stages: List[ResStage] = []
         for s, (depth, cin, inner, cout) in enumerate(self._arch.stage_dims):
             st = ResStage(in_channels=cin, inner_channels=inner, out_channels=cout, depth=depth,
@@ -598,7 +627,7 @@ class X3D(Layer):
 
     # ---- forward
     def _forward(self, x: torch.Tensor, training: bool) -> Tuple[torch.Tensor, torch.Tensor]:
-        act_dtype = self._dtype or x.dtype
+        act_dtype = self._dtype or (torch.float32 if x.dtype == torch.uint8 else x.dtype)
         out = self.conv1._forward(x, act_dtype)
         for st in self.stages:
             out = st._forward(out)
@@ -666,14 +695,17 @@ class X3D(Layer):
                 return static_in
         return None
 
-    def predict(self, batches, training: bool = False):
+    def predict(self, batches, training: bool = False, on_device=None):
         """Generator over host batches -> host probabilities: what `model.predict(dataset)` /
         `model.evaluate(dataset)` do in the reference (eval.py:83-89, Keras prefetches the next
         batch while the current one runs).  Each batch is an NDHWC numpy array or CPU tensor
         (pinned memory makes the copy asynchronous); its host->device copy is issued on a copy
         stream while the previous batch computes, the forward is one CUDA-graph replay, and the
         probabilities come back through a pinned buffer.  Yields float32 CPU tensors
-        [videos, classes] in order."""
+        [videos, classes] in order.  uint8 batches are normalised on the device (fused into the
+        stem's loader in bf16 mode).  `on_device(probs, i)`, if given, is called right after the
+        replay of batch i with the device-resident probabilities (stream-ordered: enqueue work on
+        the current stream, do not keep the tensor)."""
         self._no_training(training)
         if not torch.cuda.is_available():
             raise RuntimeError("no CUDA device: the X3D path has no CPU implementation")
@@ -714,6 +746,8 @@ class X3D(Layer):
             nxt = stage(hb, (i + 1) & 1) if hb is not None else None
             main.wait_event(cur["copied"])
             cur["g"].replay()
+            if on_device is not None:
+                on_device(cur["s_probs"], i)
             cur["host_out"].copy_(cur["s_probs"], non_blocking=True)
             cur["done"].record(main)
             self.last_logits = cur["s_logits"]
@@ -723,6 +757,45 @@ class X3D(Layer):
             pending, i = cur, i + 1
         pending["done"].synchronize()
         yield pending["host_out"].clone()
+
+    def compile(self, optimizer=None, loss=None, metrics=None, top_k: int = 5, **_):
+        """Keras `model.compile` as eval.py:62-70 uses it: the loss and the two metrics are fixed
+        (SparseCategoricalCrossentropy on probabilities, SparseCategoricalAccuracy 'acc',
+        SparseTopKCategoricalAccuracy(k) 'top_5_acc'); the arguments are accepted for source
+        compatibility, `top_k` sets k."""
+        self._top_k = int(top_k)
+        return self
+
+    def evaluate(self, dataset, group=None, return_dict: bool = True, verbose: int = 0):
+        """`model.evaluate(dataset)` of eval.py:83-89.  `dataset` yields (clips, labels): clips as
+        for `predict`, labels one int per video.  Loss and metrics are accumulated on the device
+        (x3d_eval_metrics) from the same replay that produced the probabilities; with a
+        torch.distributed `group` (or an initialised default group) the four sums are
+        all-reduced, so every rank returns the metrics of the whole sharded set."""
+        device = self._device or torch.device("cuda", torch.cuda.current_device())
+        acc = torch.zeros(4, dtype=torch.float64, device=device)
+        labels_dev: List[torch.Tensor] = []
+        k = getattr(self, "_top_k", 5)
+
+        def clips_only():
+            for clips, labels in dataset:
+                lab = torch.as_tensor(np.asarray(labels).reshape(-1), dtype=torch.int32)
+                if lab.numel() * self._num_preds != clips.shape[0]:
+                    raise ValueError(f"{clips.shape[0]} clips need {clips.shape[0] // self._num_preds} "
+                                     f"labels, got {lab.numel()}")
+                labels_dev.append(lab.to(device))
+                yield clips
+
+        def on_device(probs, i):
+            ops.eval_metrics(probs, labels_dev[i], acc, k)
+            labels_dev[i] = None
+
+        n = 0
+        for _ in self.predict(clips_only(), on_device=on_device):
+            n += 1
+            if verbose:
+                print(f"\r{n} batches", end="", flush=True)
+        return finalize_metrics(acc, group, k, return_dict)
 
     def summary(self, input_shape) -> str:
         """Keras-style table (`model.py:129-132`, dumps in `models/*/X3D_*.txt`)."""

@@ -105,6 +105,52 @@ def stem_tc_fwd(x: torch.Tensor, wc: torch.Tensor, bias: torch.Tensor) -> torch.
     return out
 
 
+def _f3(vals) -> "_lib.C.Array":
+    v = [float(x) for x in vals]
+    if len(v) != 3:
+        raise ValueError("mean / std must have 3 entries (RGB)")
+    return (_lib.C.c_float * 3)(*v)
+
+
+def normalize_u8(x: torch.Tensor, mean, std, out_dtype: torch.dtype, norm_value: float = 255.0) -> torch.Tensor:
+    """utils.normalize (reference utils.py:42-72) on uint8 NDHWC clips -> fp32 / bf16."""
+    _req(x, "x")
+    if x.dtype != torch.uint8 or x.shape[-1] != 3:
+        raise TypeError("normalize_u8 needs uint8 clips with 3 channels")
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    _launch("x3d_normalize_u8", lambda: lib().x3d_normalize_u8(
+        x.data_ptr(), out.data_ptr(), x.numel() // 3, _f3(mean), _f3(std), float(norm_value), _dt(out), _stream()))
+    return out
+
+
+def stem_tc_u8_fwd(x: torch.Tensor, mean, std, wc: torch.Tensor, bias: torch.Tensor,
+                   norm_value: float = 255.0) -> torch.Tensor:
+    """Tensor-core stem with the uint8 input stage fused into its loader; bf16 activations out."""
+    _req(x, "x")
+    if x.dtype != torch.uint8 or x.shape[-1] != 3:
+        raise TypeError("stem_tc_u8_fwd needs uint8 clips with 3 channels")
+    N, T, H, W, _ = x.shape
+    C = bias.numel()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty((N, T, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+    _launch("x3d_stem_tc_u8_fwd", lambda: lib().x3d_stem_tc_u8_fwd(
+        x.data_ptr(), _f3(mean), _f3(std), float(norm_value), wc.data_ptr(), bias.data_ptr(), out.data_ptr(),
+        N, T, H, W, C, wc.shape[0], _stream()))
+    return out
+
+
+def eval_metrics(probs: torch.Tensor, labels: torch.Tensor, acc: torch.Tensor, k: int = 5) -> None:
+    """acc[0..3] += (sum loss, top-1 hits, top-k hits, videos); eval.py:62-70."""
+    _req(probs, "probs"); _req(labels, "labels"); _req(acc, "acc")
+    if probs.dtype != torch.float32 or labels.dtype != torch.int32 or acc.dtype != torch.float64:
+        raise TypeError("eval_metrics: probs fp32, labels int32, acc fp64")
+    V, ncls = probs.shape
+    if labels.numel() != V or acc.numel() < 4:
+        raise ValueError(f"eval_metrics: {V} videos but {labels.numel()} labels / acc of {acc.numel()}")
+    _launch("x3d_eval_metrics", lambda: lib().x3d_eval_metrics(
+        probs.data_ptr(), labels.data_ptr(), acc.data_ptr(), V, ncls, int(k), _stream()))
+
+
 def pw_fwd(a: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, M: int, K: int,
            Nc: int, out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
            residual: Optional[torch.Tensor] = None, se: Optional[torch.Tensor] = None,
