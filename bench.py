@@ -32,6 +32,7 @@ WORKLOADS = {
     "m256x10": ("X3D_M", 16, 256, 10, 80, "bfloat16"),      # configs[2]  (metric config)
     "m224": ("X3D_M", 16, 224, 1, 64, "bfloat16"),          # north_star target shape
     "l356": ("X3D_L", 16, 356, 1, 32, "bfloat16"),          # configs[3]
+    "train_m224": ("X3D_M", 16, 224, 1, 32, "float32"),     # configs[4]: one training step
 }
 METRIC = "X3D-M clips/sec"
 FALLBACK_HBM_GBS, FALLBACK_BF16_TFLOPS = 6650.0, 1590.0
@@ -436,6 +437,112 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE configs[4]: one X3D-M training step (forward, backward, NCCL gradient all-reduce,
+    SGD-Nesterov) per bench step; batch 32 per GPU, 16x224x224, fp32 (the reference's default
+    precision; train.py:85-152).  value = clips trained per second over all ranks."""
+    import torch.distributed as dist
+    from x3d_tf_b200 import _lib
+    from x3d_tf_b200.arch import build_arch
+    from x3d_tf_b200.config import get_config
+    from x3d_tf_b200.synth import synthetic_weights
+    from x3d_tf_b200.training import X3DTrainer, lr_schedule
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    variant, T, S, _, clips, _ = WORKLOADS[args.workload]
+    if args.clips:
+        clips = args.clips
+    cfg = get_config(variant)
+    arch = build_arch(cfg)
+    tr = X3DTrainer(cfg, device=device, world=world).load(synthetic_weights(arch, seed=1111))
+    x = device_clips(clips, T, S, cfg, torch.float32, device, seed=1111 + rank)
+    g = torch.Generator(device=device)
+    g.manual_seed(7 + rank)
+    labels = torch.randint(0, cfg.NETWORK.NUM_CLASSES, (clips,), generator=g, device=device, dtype=torch.int32)
+    lr = lr_schedule(cfg, 0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        loss = tr.step(x, labels, lr)
+    barrier()
+    c0 = _lib.calls
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = tr.step(x, labels, lr)
+    e1.record()
+    barrier()
+    clocks = sampler.finish()
+    launches = _lib.calls - c0
+    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = clips * world * args.steps / (ms_max / 1e3)
+
+    # end to end: clips and labels come from pinned host memory every step, the loss goes back
+    host_x = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+    host_x.copy_(x.cpu())
+    host_l = labels.cpu().pin_memory()
+    n_e2e = max(3, min(args.steps, 5))
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(n_e2e):
+        x.copy_(host_x, non_blocking=True)
+        labels.copy_(host_l, non_blocking=True)
+        host_loss = tr.step(x, labels, lr).float().cpu()
+    s1.record()
+    barrier()
+    te = torch.tensor([s0.elapsed_time(s1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    hbm, _, peak_kind = peaks()
+    work = algorithmic_work(arch, T, S, S, 4)
+    fwd_bytes = sum(w["bytes"] for k, w in work.items() if k != "ab") * clips
+    if rank == 0:
+        line = {"metric": "X3D-M training clips/sec", "value": value, "unit": "clips/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{variant} training step {T}x{S}x{S}, batch {clips} per GPU, SGD-Nesterov "
+                                       f"momentum {tr.momentum}, L2, dropout {tr.dropout}, batch-statistics BN",
+                           "exchange": "one NCCL sum all-reduce of the flat fp32 gradient arena "
+                                       f"({tr.layout.size * 4 / 1e6:.2f} MB)" if world > 1 else "single rank: no exchange",
+                           "l2": f"inputs larger than L2: the clip batch is {x.numel() * 4 / 1e6:.0f} MB",
+                           "parallelism": f"dp{world}"},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": clips * world * n_e2e / (float(te.item()) / 1e3), "unit": "clips/s",
+                        "h2d_bytes_per_step": host_x.numel() * 4 + host_l.numel() * 4,
+                        "d2h_bytes_per_step": host_loss.numel() * 4, "steps": n_e2e,
+                        "api": "X3DTrainer.step on clips/labels copied from pinned host memory, per-clip losses read back"},
+                "roofline": {"kernel": "whole training step", "bound": "hbm",
+                             "achieved": 3 * fwd_bytes / (ms_max / args.steps * 1e-3) / 1e9, "peak": hbm,
+                             "unit": "GB/s", "frac": 3 * fwd_bytes / (ms_max / args.steps * 1e-3) / 1e9 / hbm,
+                             "traffic": None, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                             "how": "3 x the forward pass's algorithmic fp32 bytes (SURVEY.md 8d estimate) / step time"},
+                "cpu_baseline": None, "loss_mean": float(loss.float().mean().item())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -449,6 +556,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload.startswith("train"):
+        run_train(args)
     else:
         run_b200(args)
 

@@ -126,7 +126,12 @@ def lib() -> C.CDLL:
     return _lib
 
 
+calls = 0          # C-ABI calls that returned a status (= kernel launches); bench.py reads the delta
+
+
 def check(status: int, what: str = "") -> None:
+    global calls
+    calls += 1
     if status != 0:
         msg = lib().x3d_last_error().decode("utf-8", "replace")
         raise X3DLibError(f"{what or 'x3d call'} failed with status {status}: {msg}")
