@@ -108,24 +108,35 @@ __global__ void d2f_kernel(const double* __restrict__ in, float* __restrict__ ou
 
 // ---------------------------------------------------------------- backward-filter of a 1x1x1 conv
 // dW[k, n] += sum_m A[row(m), k] * dD[m, n]; row(m) as in x3d_pw_fwd (gather for the strided
-// shortcut).  One block = a 32x32 tile of dW over a run of rows; fp32 partial per block, fp64 atomics.
+// shortcut).  One block = a TK x TN tile of dW over a run of rows; 16 x 16 threads, each a
+// (TK/16) x (TN/16) register tile fed by 128-bit shared-memory reads (k and n interleaved by 16
+// so that a thread's values are contiguous); fp32 partial per block, fp64 atomics.
+template <int TK, int TN>
 __global__ void __launch_bounds__(256)
 pw_wgrad_kernel(const float* __restrict__ A, const float* __restrict__ dD, double* __restrict__ dW, long M,
                 int K, int N, int lda, int ldd, long rows_per_block, int gather, int Ho, int Wo, int Hi,
                 int Wi, int stride) {
-  __shared__ float sa[32][33], sd[32][33];
-  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  constexpr int RK = TK / 16, RN = TN / 16, RC = 32;       // register tile, rows per chunk
+  // element (r, k) of the A chunk lives at sa[r][(k % 16) * RK + k / 16]: thread ty reads RK contiguous floats
+  __shared__ __align__(16) float sa[RC][TK + 4];
+  __shared__ __align__(16) float sd[RC][TN + 4];
+  const int k0 = blockIdx.x * TK, n0 = blockIdx.y * TN;
   const long m0 = (long)blockIdx.z * rows_per_block;
   long m1 = m0 + rows_per_block;
   if (m1 > M) m1 = M;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 x 32
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};                      // dW[k0 + ty + 8*i][n0 + tx]
-  for (long mb = m0; mb < m1; mb += 32) {
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16
+  float acc[RK][RN];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long m = mb + ty + 8 * i;
-      float av = 0.f, dv = 0.f;
-      if (m < m1) {
+  for (int i = 0; i < RK; ++i)
+#pragma unroll
+    for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
+  for (long mb = m0; mb < m1; mb += RC) {
+    // fill: 256 threads, consecutive threads -> consecutive k (n) of one row
+    for (int e = threadIdx.x; e < RC * TK; e += 256) {
+      const int r = e / TK, k = e - r * TK;
+      const long m = mb + r;
+      float v = 0.f;
+      if (m < m1 && k0 + k < K) {
         long arow = m;
         if (gather) {
           long q = m;
@@ -133,25 +144,37 @@ pw_wgrad_kernel(const float* __restrict__ A, const float* __restrict__ dD, doubl
           const int ho = (int)(q % Ho); q /= Ho;
           arow = (q * Hi + (long)ho * stride) * Wi + (long)wo * stride;
         }
-        if (k0 + tx < K) av = A[arow * lda + k0 + tx];
-        if (n0 + tx < N) dv = dD[m * ldd + n0 + tx];
+        v = __ldg(A + arow * lda + k0 + k);
       }
-      sa[ty + 8 * i][tx] = av; sd[ty + 8 * i][tx] = dv;
+      sa[r][(k & 15) * RK + (k >> 4)] = v;
+    }
+    for (int e = threadIdx.x; e < RC * TN; e += 256) {
+      const int r = e / TN, nn = e - r * TN;
+      const long m = mb + r;
+      sd[r][(nn & 15) * RN + (nn >> 4)] = (m < m1 && n0 + nn < N) ? __ldg(dD + m * ldd + n0 + nn) : 0.f;
     }
     __syncthreads();
 #pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-      const float d = sd[r][tx];
+    for (int r = 0; r < RC; ++r) {
+      float a[RK], d[RN];
+      if (RK == 4) { const float4 v = *reinterpret_cast<const float4*>(&sa[r][ty * 4]); a[0] = v.x; a[1] = v.y; a[2 % RK] = v.z; a[3 % RK] = v.w; }
+      else { const float2 v = *reinterpret_cast<const float2*>(&sa[r][ty * 2]); a[0] = v.x; a[1] = v.y; }
+      if (RN == 4) { const float4 v = *reinterpret_cast<const float4*>(&sd[r][tx * 4]); d[0] = v.x; d[1] = v.y; d[2 % RN] = v.z; d[3 % RN] = v.w; }
+      else { const float2 v = *reinterpret_cast<const float2*>(&sd[r][tx * 2]); d[0] = v.x; d[1] = v.y; }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = fmaf(sa[r][ty + 8 * i], d, acc[i]);
+      for (int i = 0; i < RK; ++i)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a[i], d[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int k = k0 + ty + 8 * i;
-    if (k < K && n0 + tx < N) atomicAdd(dW + (long)k * N + n0 + tx, (double)acc[i]);
-  }
+  for (int i = 0; i < RK; ++i)
+#pragma unroll
+    for (int j = 0; j < RN; ++j) {
+      const int k = k0 + ty + 16 * i, nn = n0 + tx + 16 * j;
+      if (k < K && nn < N) atomicAdd(dW + (long)k * N + nn, (double)acc[i][j]);
+    }
 }
 
 // ---------------------------------------------------------------- channelwise 3x3x3 backward
@@ -189,36 +212,70 @@ dw_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float
 }
 
 // backward-filter: dw[tap,c] += sum over output pixels x[n, t+dt-1, ho*s+dh-ph, wo*s+dw-pw, c] * dy[n,t,ho,wo,c]
+// A warp (32 consecutive channels, coalesced 128-byte rows) walks whole output rows (n, t, ho)
+// left to right with the 9 x 3 input window of the current output pixel in registers: per output
+// pixel it loads 9 (stride 1) or 18 (stride 2) new values instead of 27 and runs 27 FMAs; row
+// validity (temporal / vertical zero padding) is resolved once per row.
 __global__ void __launch_bounds__(256)
 dw_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, double* __restrict__ dwt, int T, int H,
-                int W, int Ho, int Wo, int C, int stride, int ph, int pw, long opix, long pix_per_block) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int ry = threadIdx.x >> 5;
-  const long p0 = (long)blockIdx.y * pix_per_block;
-  long p1 = p0 + pix_per_block;
-  if (p1 > opix) p1 = opix;
+                int W, int Ho, int Wo, int C, int stride, int ph, int pw, long orows, long rows_per_block) {
+  const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const long r0 = (long)blockIdx.y * rows_per_block;
+  long r1 = r0 + rows_per_block;
+  if (r1 > orows) r1 = orows;
   float acc[27];
 #pragma unroll
   for (int i = 0; i < 27; ++i) acc[i] = 0.f;
   if (c < C) {
-    for (long p = p0 + ry; p < p1; p += 8) {
-      long q = p;
-      const int wo = (int)(q % Wo); q /= Wo;
+    for (long row = r0 + ry; row < r1; row += 8) {
+      long q = row;
       const int ho = (int)(q % Ho); q /= Ho;
       const int t = (int)(q % T);
       const long n = q / T;
-      const float g = dy[p * C + c];
+      const float* src[9];                  // input rows (dt, dh) of this output row, or null
 #pragma unroll
-      for (int dt = 0; dt < 3; ++dt) {
-        const int ti = t + dt - 1;
+      for (int dt = 0; dt < 3; ++dt)
 #pragma unroll
         for (int dh = 0; dh < 3; ++dh) {
-          const int hi = ho * stride + dh - ph;
+          const int ti = t + dt - 1, hi = ho * stride + dh - ph;
+          src[dt * 3 + dh] = (ti >= 0 && ti < T && hi >= 0 && hi < H)
+                                 ? x + (((n * T + ti) * H + hi) * (long)W) * C + c : nullptr;
+        }
+      const float* g = dy + row * (long)Wo * C + c;
+      float xv[9][3];
+      // columns wi = wo*stride + dw - pw; prime the window for wo = 0
 #pragma unroll
-          for (int dw = 0; dw < 3; ++dw) {
-            const int wi = wo * stride + dw - pw;
-            if (ti >= 0 && ti < T && hi >= 0 && hi < H && wi >= 0 && wi < W)
-              acc[(dt * 3 + dh) * 3 + dw] = fmaf(x[(((n * T + ti) * H + hi) * (long)W + wi) * C + c], g, acc[(dt * 3 + dh) * 3 + dw]);
+      for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int dw = 0; dw < 3; ++dw) {
+          const int wi = dw - pw;
+          xv[k][dw] = (src[k] != nullptr && wi >= 0 && wi < W) ? __ldg(src[k] + (long)wi * C) : 0.f;
+        }
+      for (int wo = 0; wo < Wo; ++wo) {
+        const float gv = __ldg(g + (long)wo * C);
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw) acc[k * 3 + dw] = fmaf(xv[k][dw], gv, acc[k * 3 + dw]);
+        if (wo + 1 < Wo) {                   // slide to the next output pixel
+          const int wn = (wo + 1) * stride - pw;          // its leftmost column
+          if (stride == 1) {
+            const int wi = wn + 2;
+            const bool ok = wi < W;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+              xv[k][0] = xv[k][1]; xv[k][1] = xv[k][2];
+              xv[k][2] = (ok && src[k] != nullptr) ? __ldg(src[k] + (long)wi * C) : 0.f;
+            }
+          } else {
+            const bool ok1 = wn + 1 < W, ok2 = wn + 2 < W;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+              xv[k][0] = xv[k][2];
+              xv[k][1] = (ok1 && src[k] != nullptr) ? __ldg(src[k] + (long)(wn + 1) * C) : 0.f;
+              xv[k][2] = (ok2 && src[k] != nullptr) ? __ldg(src[k] + (long)(wn + 2) * C) : 0.f;
+            }
           }
         }
       }
@@ -226,11 +283,11 @@ dw_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, doubl
   }
   __shared__ float sh[8][32];
   for (int tap = 0; tap < 27; ++tap) {
-    sh[ry][threadIdx.x & 31] = acc[tap];
+    sh[ry][lane] = acc[tap];
     __syncthreads();
     if (ry == 0 && c < C) {
       double s = 0.0;
-      for (int i = 0; i < 8; ++i) s += sh[i][threadIdx.x];
+      for (int i = 0; i < 8; ++i) s += sh[i][lane];
       atomicAdd(dwt + (long)tap * C + c, s);
     }
     __syncthreads();
@@ -566,11 +623,23 @@ int x3d_d2f(const double* in, float* out, int64_t n, float scale, void* stream) 
 int x3d_pw_wgrad(const float* A, const float* dD, double* dW, int64_t M, int K, int N, int lda, int ldd, int gather,
                  int Ho, int Wo, int Hi, int Wi, int stride, void* stream) {
   X3D_REQUIRE(A && dD && dW && M > 0 && K > 0 && N > 0, X3D_ERR_INVALID_ARG, "x3d_pw_wgrad: bad argument");
-  long rpb = 2048;
-  long zb = (M + rpb - 1) / rpb;
-  if (zb > 4096) { rpb = (M + 4095) / 4096; rpb = (rpb + 31) / 32 * 32; zb = (M + rpb - 1) / rpb; }
-  dim3 grid((K + 31) / 32, (N + 31) / 32, (unsigned)zb);
-  pw_wgrad_kernel<<<grid, 256, 0, S(stream)>>>(A, dD, dW, M, K, N, lda, ldd, rpb, gather, Ho, Wo, Hi, Wi, stride);
+  const bool k64 = K > 32, n64 = N > 32;
+  const int TK = k64 ? 64 : 32, TN = n64 ? 64 : 32;
+  const long tiles = (long)((K + TK - 1) / TK) * ((N + TN - 1) / TN);
+  // enough row blocks for ~8 blocks per SM in total, at least 256 rows each
+  long zb = (148L * 8 + tiles - 1) / tiles;
+  long rpb = (M + zb - 1) / zb;
+  if (rpb < 256) rpb = 256;
+  rpb = (rpb + 31) / 32 * 32;
+  zb = (M + rpb - 1) / rpb;
+  if (zb > 65535) { rpb = ((M + 65534) / 65535 + 31) / 32 * 32; zb = (M + rpb - 1) / rpb; }
+  dim3 grid((K + TK - 1) / TK, (N + TN - 1) / TN, (unsigned)zb);
+#define X3D_WG(TKK, TNN) train::pw_wgrad_kernel<TKK, TNN><<<grid, 256, 0, S(stream)>>>(A, dD, dW, M, K, N, lda, ldd, rpb, gather, Ho, Wo, Hi, Wi, stride)
+  if (k64 && n64) X3D_WG(64, 64);
+  else if (k64) X3D_WG(64, 32);
+  else if (n64) X3D_WG(32, 64);
+  else X3D_WG(32, 32);
+#undef X3D_WG
   return check_launch("x3d_pw_wgrad");
 }
 
@@ -587,12 +656,12 @@ int x3d_dw_wgrad(const float* x, const float* dy, double* dwt, int N, int T, int
                  int pad_w, void* stream) {
   X3D_REQUIRE(x && dy && dwt && N > 0 && T > 0 && H > 0 && W > 0 && C > 0 && (stride == 1 || stride == 2), X3D_ERR_INVALID_ARG, "x3d_dw_wgrad: bad argument");
   const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
-  const long opix = (long)N * T * Ho * Wo;
-  long ppb = 1024;
-  long yb = (opix + ppb - 1) / ppb;
-  if (yb > 65535) { ppb = (opix + 65534) / 65535; yb = (opix + ppb - 1) / ppb; }
+  const long orows = (long)N * T * Ho;                    // output rows; a warp walks whole rows
+  long rpb = 16;
+  long yb = (orows + rpb - 1) / rpb;
+  if (yb > 65535) { rpb = (orows + 65534) / 65535; yb = (orows + rpb - 1) / rpb; }
   dim3 grid((C + 31) / 32, (unsigned)yb);
-  dw_wgrad_kernel<<<grid, 256, 0, S(stream)>>>(x, dy, dwt, T, H, W, Ho, Wo, C, stride, pad_h, pad_w, opix, ppb);
+  dw_wgrad_kernel<<<grid, 256, 0, S(stream)>>>(x, dy, dwt, T, H, W, Ho, Wo, C, stride, pad_h, pad_w, orows, rpb);
   return check_launch("x3d_dw_wgrad");
 }
 

@@ -371,9 +371,20 @@ class X3DTrainer:
             dy5 = dy.view(N, T, Ho, Wo, ci)
             check(L.x3d_dw_wgrad(a_out.data_ptr(), dy5.data_ptr(), self.G64(q + "/b/kernel").data_ptr(), N, T, H, W,
                                  ci, s, ph, pw_, _s()), "x3d_dw_wgrad")
-            dx = torch.empty_like(a_out)
-            check(L.x3d_dw_dgrad(dy5.data_ptr(), wb.data_ptr(), dx.data_ptr(), N, T, H, W, ci, s, ph, pw_, _s()),
-                  "x3d_dw_dgrad")
+            # Backward-data through the forward kernel: for stride 1 it is the SAME convolution of dy
+            # with the taps reversed; for stride 2 dy is first zero-dilated onto the input grid (at
+            # offset 1 - pad_before per axis), which makes it the same stride-1 convolution.
+            # (x3d_dw_dgrad, the direct gather form, stays in the ABI and is what the kernel test checks
+            # this against.)
+            wflip = wb.flip(0).contiguous()
+            if s == 1:
+                g = dy5
+            else:
+                g = torch.zeros((N, T, H, W, ci), dtype=torch.float32, device=x.device)
+                off = ((1 - ph) * W + (1 - pw_)) * ci
+                check(L.x3d_strided_add(dy5.data_ptr(), g.data_ptr() + 4 * off, N * T, Ho, Wo, H, W, s, ci, _s()),
+                      "x3d_strided_add")
+            dx, _ = ops.dw_fwd(g, wflip, zero_b, 1, 1, 1, False)
             return dx.view(-1, ci)
         tape.append(dw_bwd)
         b_out = self._bn_fwd(b_pre.view(-1, ci), q + "/bn_b", False, tape)
