@@ -391,7 +391,14 @@ class X3DTrainer:
         # ---- SE (model.py:311-315) + swish (:316)
         scale = None
         if b.se_width:
-            m = ops.avgpool_fwd(b_out.view(N, Pout, ci))
+            # se_pool: per-clip column sums over the whole [T*Ho*Wo, ci] activation (fp64 atomics,
+            # thousands of CTAs; the head's avgpool kernel has one CTA per clip and 64 channels)
+            m64 = torch.zeros((N, 2, ci), dtype=torch.float64, device=x.device)
+            check(L.x3d_colreduce(b_out.data_ptr(), None, None, None, None, b_out.shape[0], ci, Pout,
+                                  m64.data_ptr(), 2, _s()), "x3d_colreduce")
+            m2 = torch.empty((N, 2, ci), dtype=torch.float32, device=x.device)
+            check(L.x3d_d2f(m64.data_ptr(), m2.data_ptr(), m2.numel(), 1.0 / Pout, _s()), "x3d_d2f")
+            m = m2[:, 0, :].contiguous()
             z = self._pw(m, self.P(q + "/se_fc1/kernel"), bias=self.P(q + "/se_fc1/bias"), relu=True)
             s_pre = self._pw(z, self.P(q + "/se_fc2/kernel"), bias=self.P(q + "/se_fc2/bias"))
             scale = self._ew(s_pre, None, 2)
