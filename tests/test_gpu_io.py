@@ -124,3 +124,29 @@ def test_evaluate_matches_oracle_metrics():
     assert abs(got["loss"] - want["loss"]) < 1e-3 * abs(want["loss"])
     with pytest.raises(ValueError):
         m.evaluate([(batches[0][0], labels[:2])])       # label count must match the videos
+
+
+def test_eval_driver_finds_checkpoint_and_evaluates(tmp_path, capsys):
+    """`python -m x3d_tf_b200.eval` flow (eval.py:26-91): `checkpoint` file -> newest bundle ->
+    load_weights(...).expect_partial() -> evaluate.  The bundle is written by X3D.save_weights with
+    seeded weights; the driver's metrics must equal a direct evaluate() of the same model on the same
+    (seeded, per-video) synthetic set, and differ from a randomly re-initialised model's."""
+    from x3d_tf_b200 import eval as E
+    from x3d_tf_b200 import model as M
+    cfg = get_config("X3D_XS")
+    M.reset_block_counters()
+    m = M.X3D(cfg, dtype="bfloat16")
+    m.set_weights_dict(synthetic_weights(build_arch(cfg), seed=77))
+    m.save_weights(str(tmp_path / "ckpt-3"))
+    (tmp_path / "checkpoint").write_text('model_checkpoint_path: "ckpt-3"\nall_model_checkpoint_paths: "ckpt-3"\n')
+    num_preds = cfg.TEST.NUM_TEMPORAL_VIEWS * cfg.TEST.NUM_SPATIAL_CROPS
+    vpb = max(cfg.TEST.BATCH_SIZE // num_preds, 1)
+    want = m.compile().evaluate(E.synthetic_batches(0, 3, vpb, num_preds, cfg.DATA.TEMP_DURATION,
+                                                    cfg.DATA.TEST_CROP_SIZE, cfg.NETWORK.NUM_CLASSES))
+    got = E.run(["--cfg", "X3D_XS", "--model_folder", str(tmp_path), "--synthetic", "3"])
+    assert got == want and got["videos"] == 3
+    assert "top_5_acc" in capsys.readouterr().out
+    # a folder without a checkpoint: the reference logs 'No checkpoint found!' and evaluates nothing
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    assert E.run(["--cfg", "X3D_XS", "--model_folder", str(empty), "--synthetic", "3"]) is None

@@ -119,17 +119,28 @@ se_mlp_kernel(const float* __restrict__ partial, int nblk, float inv_count,
               const float* __restrict__ w1, const float* __restrict__ b1,
               const float* __restrict__ w2, const float* __restrict__ b2,
               float* __restrict__ scale, int C, int Cw) {
-  extern __shared__ float sm[];      // mean[C] | z[Cw]
+  extern __shared__ float sm[];      // mean[C] | z[Cw] | red[256]
   float* mean = sm;
   float* z = sm + C;
+  float* red = z + Cw;
   const int n = blockIdx.x, tid = threadIdx.x;
   const float* p = partial + (long)n * nblk * C;
-  for (int c = tid; c < C; c += blockDim.x) {
+  // tile sums -> mean: the tiles of a channel are split over KG thread groups (independent,
+  // coalesced loads; up to 64 tiles at the stage-2 resolution), combined in fixed order
+  const int CP = C <= 64 ? 64 : (C <= 128 ? 128 : 256), KG = 256 / CP;
+  for (int cb = 0; cb < C; cb += CP) {
+    const int c = cb + (tid % CP), kg = tid / CP;
     float a = 0.f;
-    for (int k = 0; k < nblk; ++k) a += p[(long)k * C + c];
-    mean[c] = a * inv_count;
+    if (c < C)
+      for (int k = kg; k < nblk; k += KG) a += p[(long)k * C + c];
+    red[tid] = a;
+    __syncthreads();
+    if (kg == 0 && c < C) {
+      for (int g = 1; g < KG; ++g) a += red[g * CP + (tid % CP)];
+      mean[c] = a * inv_count;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
   for (int j = warp; j < Cw; j += nwarp) {
     float a = 0.f;
@@ -441,7 +452,7 @@ int x3d_se_mlp_fwd(const float* partial, int nblk, float inv_count, const float*
                    int Cw, void* stream) {
   X3D_REQUIRE(partial && w1 && b1 && w2 && b2 && scale, X3D_ERR_INVALID_ARG, "x3d_se_mlp_fwd: null pointer");
   X3D_REQUIRE(N > 0 && C > 0 && Cw > 0 && Cw <= 64 && nblk > 0, X3D_ERR_INVALID_ARG, "x3d_se_mlp_fwd: bad size");
-  se_mlp_kernel<<<N, 256, sizeof(float) * (C + Cw), S(stream)>>>(partial, nblk, inv_count, w1, b1,
+  se_mlp_kernel<<<N, 256, sizeof(float) * (C + Cw + 256), S(stream)>>>(partial, nblk, inv_count, w1, b1,
                                                                w2, b2, scale, C, Cw);
   return check_launch("x3d_se_mlp_fwd");
 }
