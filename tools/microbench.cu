@@ -66,6 +66,31 @@ __global__ void __launch_bounds__(256, 2) stencil_fma_kernel(const float2* __res
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Issue-slot test: 8 independent FFMA2 chains interleaved with NALU integer (ALU-pipe) ops per
+// 8 FFMA2.  If an FFMA2 only held the FMA pipe for its second cycle, ALU work up to one op per
+// FFMA2 would be free; if it also holds the issue port, time grows as 2*FFMA2 + ALU.
+template <int NALU>
+__global__ void __launch_bounds__(256, 2) mix_kernel(float* out, int iters, float a0, unsigned k0) {
+  float2 acc[8];
+  unsigned v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i] = make_float2(threadIdx.x * 1e-3f + i, i); v[i] = threadIdx.x * 2654435761u + i; }
+  const float2 a = make_float2(a0, a0 * 0.5f), b = make_float2(0.25f, 0.125f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] = __ffma2_rn(acc[i], a, b);
+      if (i < NALU) v[i] = (v[i] ^ k0) & 0xfffffff7u;          // one LOP3 per op, independent chains
+      if (i + 8 < NALU) v[i] = (v[i] << 16) | (v[i] >> 27);    // SHF
+    }
+  }
+  float s = 0;
+  unsigned u = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s += acc[i].x + acc[i].y; u ^= v[i]; }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s + (float)(u & 1);
+}
+
 __global__ void copy_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -110,6 +135,24 @@ int main() {
         double fmas = (double)bl * th * it2 * 72 * 2;
         if (rep) printf("%-40s %8.3f ms  %8.2f TFMA/s  (%.1f FMA/clk/SM at %d MHz nominal)\n", nm[mode], ms,
                         fmas / ms / 1e9, fmas / (ms * 1e-3) / p.multiProcessorCount / (p.clockRate * 1e3), p.clockRate / 1000);
+      }
+  }
+  {
+    const int it3 = 20000, bl = p.multiProcessorCount * 2, th = 256;   // 16 warps per SM
+    for (int nalu = 0; nalu <= 16; nalu += 4)
+      for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(e0);
+        if (nalu == 0) mix_kernel<0><<<bl, th>>>(out, it3, 1.0001f, 0x5a5a5a5au);
+        if (nalu == 4) mix_kernel<4><<<bl, th>>>(out, it3, 1.0001f, 0x5a5a5a5au);
+        if (nalu == 8) mix_kernel<8><<<bl, th>>>(out, it3, 1.0001f, 0x5a5a5a5au);
+        if (nalu == 12) mix_kernel<12><<<bl, th>>>(out, it3, 1.0001f, 0x5a5a5a5au);
+        if (nalu == 16) mix_kernel<16><<<bl, th>>>(out, it3, 1.0001f, 0x5a5a5a5au);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        const double cyc = ms * 1e-3 * p.clockRate * 1e3;               // SM cycles at nominal clock
+        const double warp_ffma2_per_smsp = (double)bl * th / 32 * it3 * 8 / p.multiProcessorCount / 4;
+        if (rep) printf("8 FFMA2 + %2d ALU ops per iteration: %8.3f ms  %.2f cycles per FFMA2 per scheduler\n", nalu, ms,
+                        cyc / warp_ffma2_per_smsp);
       }
   }
   size_t n = (size_t)1 << 26;   // 1 GiB in uint4

@@ -12,6 +12,9 @@
 // memory and written back by one TMA box store (clipped at the tensor edge) while the next frames
 // are already in flight.  All shared-memory offsets are compile-time constants; the kernel does
 // no global address arithmetic at all.
+#include <stdlib.h>
+#include <string.h>
+
 #include "tma_common.cuh"
 
 namespace x3d {
