@@ -85,10 +85,13 @@ def _model(variant, dtype, views):
     return m, cfg, W
 
 
-@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
-def test_model_uint8_clips_equal_normalised_float_clips(dtype):
-    """uint8 clips through the on-device input stage give bit-identical logits to float32 clips
-    normalised on the host the way dataloader.py does."""
+@pytest.mark.parametrize("dtype,stem_u8", [("float32", "normalize"), ("bfloat16", "normalize"),
+                                           ("bfloat16", "fused")])
+def test_model_uint8_clips_equal_normalised_float_clips(dtype, stem_u8, monkeypatch):
+    """uint8 clips through the on-device input stage (either form) give bit-identical logits to
+    float32 clips normalised on the host the way dataloader.py does."""
+    from x3d_tf_b200 import model as M
+    monkeypatch.setattr(M.Options, "stem_u8", stem_u8)
     m, cfg, W = _model("X3D_XS", dtype, 2)
     u8 = synthetic_clips_u8(4, 4, 64, 64, seed=9)
     xf = IO.normalize(u8, cfg.DATA.MEAN, cfg.DATA.STD)

@@ -17,36 +17,46 @@ __device__ __forceinline__ float normalize1(float u, float nv, float mean, float
   return __fdiv_rn(__fsub_rn(__fdiv_rn(u, nv), mean), std);
 }
 
+// A pixel value can only be one of 256 per channel, so every CTA first builds the 3 x 256 table of
+// normalised values (exact IEEE fp32 in the reference's order, rounded once for bf16 output) in
+// shared memory and the streaming loop is a byte extract + table read per element: 12 bytes in
+// (three 32-bit loads = 4 pixels), 12 values out (16-byte stores) per thread and iteration.
 template <typename TO>
 __global__ void __launch_bounds__(256)
 normalize_u8_kernel(const uint8_t* __restrict__ in, TO* __restrict__ out, int64_t pixels, const Norm nrm) {
-  // one thread = 4 pixels = 12 bytes in (three 32-bit loads), 12 values out
+  __shared__ TO lut[3][256];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    const int ch = i >> 8;
+    const float r = normalize1(static_cast<float>(i & 255), nrm.nv, nrm.mean[ch], nrm.std[ch]);
+    if (sizeof(TO) == 4) reinterpret_cast<float*>(&lut[0][0])[i] = r;
+    else reinterpret_cast<bf16*>(&lut[0][0])[i] = __float2bfloat16_rn(r);
+  }
+  __syncthreads();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int64_t groups = pixels / 4;
   for (int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups; g += stride) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(in + g * 12);
-    uint32_t w[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
-    float v[12];
+    const uint32_t w[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
+    TO v[12];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      const float u = static_cast<float>((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
-      v[i] = normalize1(u, nrm.nv, nrm.mean[i % 3], nrm.std[i % 3]);
-    }
-    TO* dst = out + g * 12;
+    for (int i = 0; i < 12; ++i) v[i] = lut[i % 3][(w[i >> 2] >> (8 * (i & 3))) & 0xffu];
+    if (sizeof(TO) == 4) {
+      float4* dst = reinterpret_cast<float4*>(out + g * 12);
+      const float* f = reinterpret_cast<const float*>(v);
 #pragma unroll
-    for (int i = 0; i < 12; i += 4) {
-      const float q[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
-      st4(dst + i, q);
+      for (int i = 0; i < 3; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+    } else {
+      // 24 bytes: 8-byte aligned for every g, 16-byte aligned for even g
+      uint2* dst = reinterpret_cast<uint2*>(out + g * 12);
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) dst[i] = make_uint2(u[2 * i], u[2 * i + 1]);
     }
   }
   // tail (pixels % 4) by the first threads of block 0
   if (blockIdx.x == 0) {
     const int64_t done = groups * 4;
-    for (int64_t e = done * 3 + threadIdx.x; e < pixels * 3; e += blockDim.x) {
-      const float r = normalize1(static_cast<float>(in[e]), nrm.nv, nrm.mean[e % 3], nrm.std[e % 3]);
-      if (sizeof(TO) == 4) reinterpret_cast<float*>(out)[e] = r;
-      else reinterpret_cast<bf16*>(out)[e] = __float2bfloat16_rn(r);
-    }
+    for (int64_t e = done * 3 + threadIdx.x; e < pixels * 3; e += blockDim.x) out[e] = lut[e % 3][in[e]];
   }
 }
 

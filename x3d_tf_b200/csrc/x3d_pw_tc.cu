@@ -15,6 +15,8 @@
 //
 // Reference call sites replaced: Bottleneck.a/bn_a/relu (model.py:306-308), Bottleneck.c/bn_c +
 // ResBlock add/relu (model.py:317-318,389-392), conv5 (model.py:117).
+#include <stdlib.h>
+
 #include "tma_common.cuh"
 
 namespace x3d {
@@ -334,6 +336,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(w[i][0]), "=r"(w[i][1]), "=r"(w[i][2]), "=r"(w[i][3])
                          : "r"(addr0 + i * (32 * 128)));
+          float2 hs[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hs[j] = __fmul2_rn(sc[j], make_float2(0.5f, 0.5f));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             if (p.se && !one_clip) {
@@ -344,20 +349,28 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
                 sc[0] = make_float2(s0.x, s0.y); sc[1] = make_float2(s0.z, s0.w);
                 sc[2] = make_float2(s1.x, s1.y); sc[3] = make_float2(s1.z, s1.w);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hs[j] = __fmul2_rn(sc[j], make_float2(0.5f, 0.5f));
               }
             }
+            if (p.swish) {
+              // swish(s x) = h + h tanh(h) with h = (s/2) x: one multiply, two MUFU, one FMA per pair
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 a = __fmul2_rn(make_float2(__uint_as_float(w[i][j] << 16), __uint_as_float(w[i][j] & 0xffff0000u)), sc[j]);
-              if (p.swish) {
-                const float2 hx = __fmul2_rn(a, make_float2(0.5f, 0.5f));
+              for (int j = 0; j < 4; ++j) {
+                const float2 h = __fmul2_rn(make_float2(__uint_as_float(w[i][j] << 16), __uint_as_float(w[i][j] & 0xffff0000u)), hs[j]);
                 float2 t;
-                asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(hx.x));
-                asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(hx.y));
-                a = __fmul2_rn(a, __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f)));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+                __nv_bfloat162 t2 = __float22bfloat162_rn(__ffma2_rn(h, t, h));
+                w[i][j] = *reinterpret_cast<uint32_t*>(&t2);
               }
-              __nv_bfloat162 t2 = __float22bfloat162_rn(a);
-              w[i][j] = *reinterpret_cast<uint32_t*>(&t2);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 t2 = __float22bfloat162_rn(__fmul2_rn(
+                    make_float2(__uint_as_float(w[i][j] << 16), __uint_as_float(w[i][j] & 0xffff0000u)), sc[j]));
+                w[i][j] = *reinterpret_cast<uint32_t*>(&t2);
+              }
             }
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr0 + i * (32 * 128)), "r"(w[i][0]), "r"(w[i][1]), "r"(w[i][2]), "r"(w[i][3]) : "memory");
           }

@@ -231,6 +231,9 @@ class Options:
     # B200 it is only break-even with the two-kernel path today (profiles/r01_fused_expand_dw.md),
     # so it is opt-in.
     fuse_expand = False
+    # uint8 clips in bf16 mode: "normalize" = x3d_normalize_u8 then the ordinary stem;
+    # "fused" = x3d_stem_tc_u8_fwd (the stem's loader reads bytes through a lookup table)
+    stem_u8 = "normalize"
 
 
 def _use_tc() -> bool:
@@ -283,8 +286,10 @@ class X3D_Stem(Layer):
             if self.input_norm is None:
                 raise ValueError("uint8 clips need input_norm = (mean, std) (cfg.DATA.MEAN / cfg.DATA.STD)")
             mean, std = self.input_norm
-            if tc:
+            if tc and Options.stem_u8 == "fused":
                 return ops.stem_tc_u8_fwd(x, mean, std, d["wc"], d["bias"])
+            # default: one streaming pass (table lookup, ~0.15 ms for 80 clips of 16x256x256) and the
+            # ordinary stem; measured faster than byte gathers inside the stem's im2col loader
             x = ops.normalize_u8(x, mean, std, out_dtype)
         if tc:
             return ops.stem_tc_fwd(x, d["wc"], d["bias"])
@@ -659,7 +664,7 @@ class X3D(Layer):
         first use (after one eager run that warms lazy CUDA state).  Slots > 0 are extra captures
         over their own input/output buffers that share slot 0's memory pool (replays are
         stream-ordered), used by `predict` to overlap the H2D copy of the next batch."""
-        key = (tuple(shape), dtype, str(device), Options.pointwise, Options.stem, slot)
+        key = (tuple(shape), dtype, str(device), Options.pointwise, Options.stem, Options.stem_u8, slot)
         if key not in self._graphs:
             static_in = torch.zeros(tuple(shape), dtype=dtype, device=device)
             self._forward(static_in, training)
