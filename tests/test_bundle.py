@@ -92,3 +92,58 @@ def test_scalar_and_empty_dim_entries():
     assert tb.BundleEntry.parse(e.serialize()) == e
     e = tb.BundleEntry(dtype=tb.DT_FLOAT, shape=(3, 0, 2), offset=0, size=0, crc32c=1)
     assert tb.BundleEntry.parse(e.serialize()) == e
+
+
+def test_optimizer_state_round_trip_and_tf_known_answers(tmp_path):
+    """The optimizer part of a Keras checkpoint (utils.py:128-132): our writer
+    must produce the entries the shipped X3D-M index holds for the same values (masked CRC-32C
+    known answers), and the reader must give the slots back under their variable paths."""
+    from x3d_tf_b200 import tf_bundle as B
+    rng = np.random.default_rng(0)
+    weights = {"conv1/conv_s/kernel": rng.normal(size=(1, 3, 3, 3, 24)).astype(np.float32),
+               "conv1/bn/moving_mean": rng.normal(size=24).astype(np.float32)}
+    slots = {"conv1/conv_s/kernel": rng.normal(size=(1, 3, 3, 3, 24)).astype(np.float32)}
+    tensors = dict(weights)
+    tensors.update(B.optimizer_tensors(1876480, 0.05, 0.9, slots))
+    prefix = str(tmp_path / "ckpt-7")
+    B.write_bundle(prefix, tensors)
+    rd = B.BundleReader(prefix)
+    entries = {k: B.BundleEntry.parse(v) for k, v in B.read_index(prefix + ".index").items() if k}
+    sfx = B.VAR_SUFFIX
+    assert entries["optimizer/momentum" + sfx].crc32c == 0xdfc7ebfd          # float32 0.9
+    assert entries["optimizer/decay" + sfx].crc32c == 0x3a117ba6             # float32 0.0
+    assert entries["optimizer/iter" + sfx].crc32c == 0x948df8a0              # int64 1 876 480 (X3D-M)
+    assert "conv1/conv_s/kernel/.OPTIMIZER_SLOT/optimizer/momentum" + sfx in rd
+    st = B.load_optimizer_state(prefix)
+    assert st["iter"] == 1876480 and abs(st["momentum"] - 0.9) < 1e-7 and abs(st["learning_rate"] - 0.05) < 1e-8
+    assert list(st["slots"]) == ["conv1/conv_s/kernel"]
+    assert np.array_equal(st["slots"]["conv1/conv_s/kernel"], slots["conv1/conv_s/kernel"])
+    # model variables are still read without the optimizer entries (expect_partial semantics)
+    got = B.load_model_variables(prefix)
+    assert sorted(got) == sorted(weights) and np.array_equal(got["conv1/bn/moving_mean"], weights["conv1/bn/moving_mean"])
+    assert B.latest_checkpoint(str(tmp_path)).endswith("ckpt-7")
+
+
+def test_train_driver_host_logic(tmp_path):
+    """Epoch from the checkpoint name (train.py:133), the LR schedule (train.py:114-125) and the
+    shuffled file batches of the training driver."""
+    import math
+    from x3d_tf_b200 import train as T
+    from x3d_tf_b200.config import get_config
+    assert T.epoch_of_checkpoint("/a/b/ckpt-17") == 17
+    cfg = get_config("X3D_M")
+    t = cfg.TRAIN
+    for e in (0, 1, t.WARMUP_EPOCHS, t.WARMUP_EPOCHS + 1, 100, t.EPOCHS - 1):
+        want = (t.BASE_LR * 0.5 * (math.cos(math.pi * e / t.EPOCHS) + 1) if e > t.WARMUP_EPOCHS
+                else t.WARMUP_LR + e * (t.BASE_LR - t.WARMUP_LR) / t.WARMUP_EPOCHS)
+        assert abs(T.lr_for_epoch(cfg, e) - want) < 1e-12
+    items = []
+    for i in range(5):
+        np.save(tmp_path / f"c{i}.npy", np.full((2, 1, 2, 2, 3) if i % 2 else (1, 2, 2, 3), i, np.uint8))
+        items.append((str(tmp_path / f"c{i}.npy"), i))
+    batches = list(T.file_clip_batches(items, 2, np.random.default_rng(0)))
+    assert len(batches) == 2 and all(b[0].shape == (2, 1, 2, 2, 3) for b in batches)
+    for clips, labels in batches:                          # the label travels with its clip
+        assert [int(c.flat[0]) for c in clips] == labels.tolist()
+    syn = list(T.synthetic_clip_batches(5, 2, 1, 4, 400, 3))
+    assert len(syn) == 2 and syn[0][0].dtype == np.uint8 and syn[0][1].dtype == np.int32

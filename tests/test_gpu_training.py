@@ -128,3 +128,53 @@ def test_dropout_mask_statistics():
     vals = torch.unique(m).cpu().tolist()
     assert vals == [0.0, 2.0]
     assert abs(float((m > 0).float().mean().item()) - 0.5) < 5e-3
+
+
+def test_checkpoint_round_trip_with_optimizer_slots(tmp_path):
+    """save_checkpoint -> load_checkpoint restores weights, moving statistics, momentum slots and
+    the iteration counter exactly (utils.py:128-132 / train.py:131-136), and the restored trainer
+    takes the same next step."""
+    from x3d_tf_b200.training import X3DTrainer
+    cfg, W, x, labels, mask, tr = _setup("X3D_XS", dropout=0.0)
+    xd, ld = torch.from_numpy(x).cuda(), torch.from_numpy(labels).cuda()
+    tr.step(xd, ld, 1e-2)
+    tr.step(xd, ld, 1e-2)
+    prefix = str(tmp_path / "ckpt-2")
+    tr.save_checkpoint(prefix, lr=1e-2)
+    tr2 = X3DTrainer(cfg)
+    st = tr2.load_checkpoint(prefix, strict_slots=True)
+    assert st["iter"] == 2 and tr2.iteration == 2 and abs(st["momentum"] - 0.9) < 1e-7
+    assert torch.equal(tr2.w, tr.w) and torch.equal(tr2.v, tr.v)
+    Wa, Wb = tr.weights(), tr2.weights()               # real channels (padding restarts at 0 / 1)
+    for k in tr.moving:
+        assert np.array_equal(Wa[k], Wb[k])
+    tr.step(xd, ld, 5e-3)
+    tr2.step(xd, ld, 5e-3)
+    torch.cuda.synchronize()
+    # fp64 atomics order may differ between the two runs: agreement to fp32 rounding, not bitwise
+    assert float((tr2.w - tr.w).abs().max()) <= 1e-6 * float(tr.w.abs().max())
+    # the inference model reads the same checkpoint (optimizer entries ignored: expect_partial)
+    from x3d_tf_b200 import model as M
+    M.reset_block_counters()
+    m = M.X3D(cfg, dtype="float32")
+    status = m.load_weights(prefix)
+    status.expect_partial()
+    assert not status.missing
+
+
+def test_train_driver_epochs_checkpoints_and_resume(tmp_path, capsys):
+    """`python -m x3d_tf_b200.train` flow (train.py:128-152): per-epoch LR, ckpt-{epoch} files with
+    optimizer state, resume at the epoch parsed from the newest checkpoint's name."""
+    from x3d_tf_b200 import train as T
+    from x3d_tf_b200 import tf_bundle as B
+    args = ["--config", "X3D_XS", "--model_dir", str(tmp_path), "--synthetic", "8", "--batch_size", "2",
+            "--crop_size", "64", "--steps_per_epoch", "2"]
+    r = T.run(args + ["--epochs", "2"])
+    assert [h["epoch"] for h in r["history"]] == [1, 2] and r["iteration"] == 4
+    assert all(np.isfinite(h["loss"]) for h in r["history"])
+    assert r["history"][0]["lr"] != r["history"][1]["lr"]                  # warm-up: lr changes every epoch
+    assert B.latest_checkpoint(str(tmp_path)).endswith("ckpt-2")
+    assert B.load_optimizer_state(str(tmp_path / "ckpt-2"))["iter"] == 4
+    r2 = T.run(args + ["--epochs", "3"])                                   # resumes at epoch 2, runs epoch 3 only
+    assert [h["epoch"] for h in r2["history"]] == [3] and r2["iteration"] == 6
+    assert "Found checkpoint" in capsys.readouterr().err

@@ -345,6 +345,47 @@ def load_model_variables(prefix: str, verify: bool = True,
     return out
 
 
+SLOT_INFIX = "/.OPTIMIZER_SLOT/optimizer/momentum"
+
+
+def load_optimizer_state(prefix: str, verify: bool = True) -> Dict[str, object]:
+    """Optimizer part of a Keras checkpoint written by `ModelCheckpoint` (`utils.py:128-132`):
+    `optimizer/{iter,learning_rate,momentum,decay}` and the SGD momentum slots
+    `<variable>/.OPTIMIZER_SLOT/optimizer/momentum`.  Returns
+    {"iter": int, "learning_rate": float|None, "momentum": float|None, "decay": float|None,
+     "slots": {variable path -> float32 array}}; missing pieces are None / empty."""
+    rd = BundleReader(prefix)
+    out: Dict[str, object] = {"iter": None, "learning_rate": None, "momentum": None, "decay": None, "slots": {}}
+    for k in rd.keys():
+        if not k.endswith(VAR_SUFFIX):
+            continue
+        name = k[:-len(VAR_SUFFIX)]
+        if name.startswith("optimizer/"):
+            v = rd.tensor(k, verify)
+            field = name[len("optimizer/"):]
+            if field == "iter":
+                out["iter"] = int(np.asarray(v).reshape(-1)[0])
+            elif field in out:
+                out[field] = float(np.asarray(v).reshape(-1)[0])
+        elif name.endswith(SLOT_INFIX):
+            out["slots"][name[:-len(SLOT_INFIX)]] = rd.tensor(k, verify)
+    return out
+
+
+def optimizer_tensors(iteration: int, learning_rate: float, momentum: float, slots: Dict[str, np.ndarray],
+                      decay: float = 0.0) -> Dict[str, np.ndarray]:
+    """The same keys as a dict for `write_bundle` (merged with the model variables)."""
+    out: Dict[str, np.ndarray] = {
+        "optimizer/iter": np.asarray(iteration, np.int64),
+        "optimizer/learning_rate": np.asarray(learning_rate, np.float32),
+        "optimizer/momentum": np.asarray(momentum, np.float32),
+        "optimizer/decay": np.asarray(decay, np.float32),
+    }
+    for name, v in slots.items():
+        out[name + SLOT_INFIX] = np.asarray(v, np.float32)
+    return out
+
+
 # ------------------------------------------------------------------------------ writer
 class _BlockBuilder:
     def __init__(self, restart_interval: int = 16):

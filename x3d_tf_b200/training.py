@@ -182,6 +182,36 @@ class X3DTrainer:
         """Momentum slots (the `.OPTIMIZER_SLOT/optimizer/momentum` variables of a Keras checkpoint)."""
         return {n: self._from_dev_layout(n, self.layout.view(self.v, n)) for n in self.layout.slots}
 
+    # ------------------------------------------------------------------ checkpoints (utils.py:128-132)
+    def save_checkpoint(self, prefix: str, lr: float = 0.0) -> None:
+        """What Keras `ModelCheckpoint(.../ckpt-{epoch})` writes for this model and optimizer: the
+        model variables, `optimizer/{iter,learning_rate,momentum,decay}` and one momentum slot per
+        trainable variable (key map: SURVEY.md Appendix C.4), as a TF tensor bundle plus the
+        `checkpoint` state file.  (No object graph: readable by name, see tf_bundle.write_bundle.)"""
+        from . import tf_bundle
+        tensors = dict(self.weights())
+        tensors.update(tf_bundle.optimizer_tensors(self.iteration, lr, self.momentum, self.velocity()))
+        tf_bundle.write_bundle(prefix, tensors)
+
+    def load_checkpoint(self, prefix: str, strict_slots: bool = False) -> dict:
+        """Restore weights, moving statistics, momentum slots and the iteration counter from a
+        checkpoint written by `save_checkpoint` or by the reference's `train.py`.  A checkpoint
+        without optimizer state (`model.save_weights`) restarts the momentum at zero unless
+        `strict_slots`."""
+        from . import tf_bundle
+        self.load(tf_bundle.load_model_variables(prefix))
+        st = tf_bundle.load_optimizer_state(prefix)
+        slots = st["slots"]
+        self.v.zero_()
+        for name in self.layout.slots:
+            if name in slots:
+                self.layout.view(self.v, name).copy_(torch.from_numpy(self._to_dev_layout(name, slots[name])))
+            elif strict_slots:
+                raise KeyError(f"{prefix}: no momentum slot for {name}")
+        if st["iter"] is not None:
+            self.iteration = int(st["iter"])
+        return st
+
     # ------------------------------------------------------------------ primitive ops
     def _pw(self, x2d, w, bias=None, relu=False, gather=None, M=None):
         K, N = w.shape
