@@ -103,6 +103,13 @@ int x3d_dw_partial_blocks(int T, int H, int W, int C, int stride, int dtype);
 int x3d_dw3x3x3_fwd(const void* in, const float* w, const float* bias, void* out,
                     float* se_partial, int N, int T, int H, int W, int C, int stride,
                     int pad_h, int pad_w, int dtype, void* stream);
+/* The same with the activation that follows bn_b fused into the epilogue: act = 1 applies swish
+ * (model.py:316) to the output.  Only for blocks WITHOUT Squeeze-Excitation (se_partial must be
+ * NULL): with SE the per-clip scale has to be applied before the swish, which the projection GEMM's
+ * prologue does.  act = 0 is x3d_dw3x3x3_fwd. */
+int x3d_dw3x3x3_act_fwd(const void* in, const float* w, const float* bias, void* out,
+                        float* se_partial, int N, int T, int H, int W, int C, int stride,
+                        int pad_h, int pad_w, int dtype, int act, void* stream);
 
 /* ---- Squeeze-Excitation MLP: se_pool/se_fc1/se_fc2, model.py:311-314 ------------------------
  *   mean[n,c] = inv_count * sum_b partial[n,b,c];  z = relu(mean.w1 + b1);  scale = sigmoid(z.w2 + b2)

@@ -103,6 +103,12 @@ def test_channelwise(dtype, N, T, H, W, C, stride):
     out2, p2 = _ops().dw_fwd(to_dev(x, dtype), to_dev(k.reshape(27, C)), to_dev(bias), stride,
                              ph, pw, False)
     assert p2 is None and torch.equal(out, out2)
+    # swish fused into the epilogue (blocks without SE, model.py:316): swish of the unrounded output
+    out3, _ = _ops().dw_fwd(to_dev(x, dtype), to_dev(k.reshape(27, C)), to_dev(bias), stride,
+                            ph, pw, False, swish=True)
+    assert_close(to_np(out3), want / (1.0 + np.exp(-want)), dtype, "channelwise + swish")
+    with pytest.raises(ValueError):
+        _ops().dw_fwd(to_dev(x, dtype), to_dev(k.reshape(27, C)), to_dev(bias), stride, ph, pw, True, swish=True)
 
 
 # ------------------------------------------------------------------------------- fused expand + channelwise

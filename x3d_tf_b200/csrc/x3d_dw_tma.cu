@@ -35,6 +35,7 @@ struct Params {
   int slot_bytes;        // ring pitch: bytes of one staged frame tile rounded up to 128
   int box_bytes;         // exact bytes one TMA box copy delivers
   int stage_bytes;       // output staging tile Q*SW*CH elements, rounded up to 128
+  int act;               // 1: swish applied to the output (blocks without SE, model.py:316)
 };
 
 // shared-memory reads by 32-bit shared-space address (keeps LDS, never generic LD)
@@ -152,6 +153,17 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
   // (rows >= Ho, columns >= Wo and channels >= Cs are clipped by the TMA unit).
   auto stage_out = [&](float2 (&A)[SW], int t_out) {
     const uint32_t dst = stage_s + (t_out % kSlots) * p.stage_bytes + soff;
+    if (p.act) {
+      // swish(a) = h + h tanh(h), h = a / 2: one multiply, two MUFU, one FMA per channel pair
+#pragma unroll
+      for (int j = 0; j < SW; ++j) {
+        const float2 h = __fmul2_rn(A[j], make_float2(0.5f, 0.5f));
+        float2 t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+        A[j] = __ffma2_rn(h, t, h);
+      }
+    }
     if (in_slot) {
 #pragma unroll
       for (int j = 0; j < SW; ++j) Pack<T>::sts2(dst + j * PS, A[j]);
@@ -332,6 +344,14 @@ extern "C" int x3d_dw_partial_blocks(int T, int H, int W, int C, int stride, int
 extern "C" int x3d_dw3x3x3_fwd(const void* in, const float* w, const float* bias, void* out,
                                float* se_partial, int N, int T, int H, int W, int C, int stride,
                                int pad_h, int pad_w, int dtype, void* stream) {
+  return x3d_dw3x3x3_act_fwd(in, w, bias, out, se_partial, N, T, H, W, C, stride, pad_h, pad_w, dtype, 0, stream);
+}
+
+extern "C" int x3d_dw3x3x3_act_fwd(const void* in, const float* w, const float* bias, void* out,
+                                   float* se_partial, int N, int T, int H, int W, int C, int stride,
+                                   int pad_h, int pad_w, int dtype, int act, void* stream) {
+  X3D_REQUIRE(act == 0 || (act == 1 && se_partial == nullptr), X3D_ERR_INVALID_ARG,
+              "x3d_dw3x3x3_act_fwd: act=%d (0, or 1 = swish without SE sums: with SE the scale comes first)", act);
   X3D_REQUIRE(in && w && bias && out, X3D_ERR_INVALID_ARG, "x3d_dw3x3x3_fwd: null pointer");
   X3D_REQUIRE(C > 0 && C % 8 == 0, X3D_ERR_INVALID_ARG, "x3d_dw3x3x3_fwd: C=%d not a multiple of 8", C);
   X3D_REQUIRE(stride == 1 || stride == 2, X3D_ERR_UNSUPPORTED, "x3d_dw3x3x3_fwd: stride %d", stride);
@@ -378,6 +398,7 @@ extern "C" int x3d_dw3x3x3_fwd(const void* in, const float* w, const float* bias
   p.Q = pl.Q; p.tiles_w = pl.tiles_w; p.tiles = pl.tiles_w * pl.tiles_h;
   p.pad_h = pad_h; p.pad_w = pad_w; p.slot_bytes = pl.slot_bytes; p.box_bytes = pl.box_bytes;
   p.stage_bytes = pl.stage_bytes;
+  p.act = act;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == X3D_BF16)
     return stride == 1 ? dwt::dispatch<bf16, 1>(tm, tmo, p, pl, N, st) : dwt::dispatch<bf16, 2>(tm, tmo, p, pl, N, st);

@@ -234,6 +234,10 @@ class Options:
     # uint8 clips in bf16 mode: "normalize" = x3d_normalize_u8 then the ordinary stem;
     # "fused" = x3d_stem_tc_u8_fwd (the stem's loader reads bytes through a lookup table)
     stem_u8 = "normalize"
+    # blocks without SE: apply swish in the channelwise kernel's epilogue (x3d_dw3x3x3_act_fwd)
+    # instead of the projection GEMM's prologue.  Measured at 80 clips of 16x256^2: c 2.80 -> 2.51 ms
+    # but b 4.93 -> 5.14 ms (the stencil is the FMA/issue-bound kernel), net 0.3 %: off by default.
+    swish_in_dw = False
 
 
 def _use_tc() -> bool:
@@ -397,11 +401,15 @@ class Bottleneck(Layer):
             ops.Profiler.tag = "ab"
             b, partial = ops.expand_dw_fwd(x, d["a"].wp, d["a"].bias, d["wb"], d["bb"],
                                            self.stride, ph, pw, self.has_se)
+            swish_in_b = False
         else:
             ops.Profiler.tag = "a"
             a = d["a"].run(x, N * T * H * W, use_tc=tc, relu=True).view(N, T, H, W, ci)
             ops.Profiler.tag = "b"
-            b, partial = ops.dw_fwd(a, d["wb"], d["bb"], self.stride, ph, pw, self.has_se)
+            # blocks without SE: the swish that follows bn_b goes into the stencil's epilogue, so the
+            # projection GEMM runs without its transform warps (its fastest form)
+            swish_in_b = Options.swish_in_dw and not self.has_se
+            b, partial = ops.dw_fwd(a, d["wb"], d["bb"], self.stride, ph, pw, self.has_se, swish=swish_in_b)
             del a
         _, _, Ho, Wo, _ = b.shape
         se = None
@@ -410,7 +418,7 @@ class Bottleneck(Layer):
             se = ops.se_mlp_fwd(partial, T * Ho * Wo, d["w1"], d["b1"], d["w2"], d["b2"])
         ops.Profiler.tag = "c"
         out = d["c"].run(b, N * T * Ho * Wo, use_tc=tc, se=se, rows_per_clip=T * Ho * Wo,
-                         swish=True, residual=residual, relu=relu)
+                         swish=not swish_in_b, residual=residual, relu=relu)
         return out.view(N, T, Ho, Wo, _pad8(self.out_channels))
 
     def call(self, input, training: bool = False):
@@ -664,7 +672,7 @@ class X3D(Layer):
         first use (after one eager run that warms lazy CUDA state).  Slots > 0 are extra captures
         over their own input/output buffers that share slot 0's memory pool (replays are
         stream-ordered), used by `predict` to overlap the H2D copy of the next batch."""
-        key = (tuple(shape), dtype, str(device), Options.pointwise, Options.stem, Options.stem_u8, slot)
+        key = (tuple(shape), dtype, str(device), Options.pointwise, Options.stem, Options.stem_u8, Options.swish_in_dw, slot)
         if key not in self._graphs:
             static_in = torch.zeros(tuple(shape), dtype=dtype, device=device)
             self._forward(static_in, training)

@@ -224,8 +224,11 @@ def head_fc_fwd(a: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor],
 
 
 def dw_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: int, pad_h: int,
-           pad_w: int, want_se: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+           pad_w: int, want_se: bool, swish: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """`swish`: apply the activation that follows bn_b in the kernel's epilogue (blocks without SE)."""
     _req(x, "x")
+    if swish and want_se:
+        raise ValueError("swish can only be fused when no SE sums are requested")
     N, T, H, W, C = x.shape
     Ho, Wo = -(-H // stride), -(-W // stride)
     out = torch.empty((N, T, Ho, Wo, C), dtype=x.dtype, device=x.device)
@@ -235,8 +238,8 @@ def dw_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: int, pa
         if nblk <= 0:
             raise _lib.X3DLibError("x3d_dw_partial_blocks rejected the shape")
         partial = torch.empty((N, nblk, C), dtype=torch.float32, device=x.device)
-    _launch("x3d_dw3x3x3_fwd", lambda: lib().x3d_dw3x3x3_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(),
-                                _ptr(partial), N, T, H, W, C, stride, pad_h, pad_w, _dt(x),
+    _launch("x3d_dw3x3x3_fwd", lambda: lib().x3d_dw3x3x3_act_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                _ptr(partial), N, T, H, W, C, stride, pad_h, pad_w, _dt(x), int(swish),
                                 _stream()))
     return out, partial
 
