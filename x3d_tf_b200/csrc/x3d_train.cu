@@ -296,28 +296,38 @@ dw_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, doubl
 
 // ---------------------------------------------------------------- stem pieces (training form)
 // conv_s: 1x3x3, stride (1,2,2), explicit zero pad 1 on H and W, 3 -> C (model.py:161-184,203-204)
+// One thread = one output pixel x 4 channels (128-bit weight loads and stores); blockIdx.x = output
+// row (n*T*Ho + ho), so the only per-element division left is by the small C/4.
 __global__ void __launch_bounds__(256)
 stem_convs_fwd_kernel(const float* __restrict__ in, const float* __restrict__ ws, float* __restrict__ out, int H,
-                      int W, int Ho, int Wo, int C, long total) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    long q = i / C;
-    const int wo = (int)(q % Wo); q /= Wo;
-    const int ho = (int)(q % Ho);
-    const long nt = q / Ho;
-    float acc = 0.f;
+                      int W, int Ho, int Wo, int C) {
+  const int C4 = C >> 2;
+  const long row = blockIdx.x;
+  const int ho = (int)(row % Ho);
+  const long nt = row / Ho;
+  for (int e = threadIdx.x; e < Wo * C4; e += blockDim.x) {
+    const int wo = e / C4, c = (e - wo * C4) << 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
     for (int dh = 0; dh < 3; ++dh) {
       const int hi = 2 * ho + dh - 1;
       if (hi < 0 || hi >= H) continue;
+#pragma unroll
       for (int dw = 0; dw < 3; ++dw) {
         const int wi = 2 * wo + dw - 1;
         if (wi < 0 || wi >= W) continue;
         const float* px = in + ((nt * H + hi) * (long)W + wi) * 3;
         const float* wk = ws + ((dh * 3 + dw) * 3) * C + c;
-        acc = fmaf(px[0], wk[0], acc); acc = fmaf(px[1], wk[C], acc); acc = fmaf(px[2], wk[2 * C], acc);
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float x = __ldg(px + ci);
+          const float4 w = __ldg(reinterpret_cast<const float4*>(wk + ci * C));
+          acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y);
+          acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
+        }
       }
     }
-    out[i] = acc;
+    *reinterpret_cast<float4*>(out + (row * Wo + wo) * (long)C + c) = acc;
   }
 }
 // backward-filter of conv_s: dws[(dh*3+dw)*3+ci, c] += sum in[...] * ds[n,t,ho,wo,c]
@@ -368,22 +378,30 @@ stem_convs_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ 
 }
 // conv_t: kt x1x1 channelwise over T with zero pad kt/2 (model.py:170-175,187-194,205-206).
 // out[n,t,p,c] = sum_d in[n, t+d-kt/2, p, c] * wt[d',c],  d' = flip ? kt-1-d : d  (flip = backward-data)
+// One thread = 4 channels of one pixel; a block works inside one frame (n*T + t): 128-bit loads, one
+// small modulo per element instead of three 64-bit divisions.
 __global__ void __launch_bounds__(256)
 tconv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ wt, float* __restrict__ out, int T,
-                 long P, int C, int kt, int flip, long total) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    long q = i / C;
-    const long pp = q % P; q /= P;
-    const int t = (int)(q % T);
-    const long n = q / T;
-    float acc = 0.f;
+                 long P, int C, int kt, int flip, int blocks_per_frame) {
+  const int C4 = C >> 2;
+  const long frame4 = P * C4;                       // float4 elements per frame
+  const long nt = blockIdx.x / blocks_per_frame;
+  const int bx = blockIdx.x - (int)(nt * blocks_per_frame);
+  const int t = (int)(nt % T);
+  const float4* in4 = reinterpret_cast<const float4*>(in);
+  float4* out4 = reinterpret_cast<float4*>(out);
+  for (long e = (long)bx * blockDim.x + threadIdx.x; e < frame4; e += (long)blocks_per_frame * blockDim.x) {
+    const int c = (int)(e % C4) << 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int d = 0; d < kt; ++d) {
       const int ti = t + d - kt / 2;
       if (ti < 0 || ti >= T) continue;
-      acc = fmaf(in[((n * T + ti) * P + pp) * C + c], wt[(flip ? kt - 1 - d : d) * C + c], acc);
+      const float4 x = __ldg(in4 + (nt + d - kt / 2) * frame4 + e);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wt + (flip ? kt - 1 - d : d) * C + c));
+      acc.x = fmaf(x.x, w.x, acc.x); acc.y = fmaf(x.y, w.y, acc.y);
+      acc.z = fmaf(x.z, w.z, acc.z); acc.w = fmaf(x.w, w.w, acc.w);
     }
-    out[i] = acc;
+    out4[nt * frame4 + e] = acc;
   }
 }
 // dwt[d,c] += sum s[n, t+d-kt/2, p, c] * dy[n,t,p,c]
@@ -668,8 +686,9 @@ int x3d_dw_wgrad(const float* x, const float* dy, double* dwt, int N, int T, int
 int x3d_stem_convs_fwd(const float* in, const float* ws, float* out, int N, int T, int H, int W, int C, void* stream) {
   X3D_REQUIRE(in && ws && out && N > 0 && T > 0 && H > 0 && W > 0 && C > 0, X3D_ERR_INVALID_ARG, "x3d_stem_convs_fwd: bad argument");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  const long total = (long)N * T * Ho * Wo * C;
-  stem_convs_fwd_kernel<<<ew_blocks(total), 256, 0, S(stream)>>>(in, ws, out, H, W, Ho, Wo, C, total);
+  const long rows = (long)N * T * Ho;
+  X3D_REQUIRE(C % 4 == 0 && rows <= 2147483647L, X3D_ERR_UNSUPPORTED, "x3d_stem_convs_fwd: C=%d must be a multiple of 4 (and N*T*Ho < 2^31)", C);
+  stem_convs_fwd_kernel<<<(unsigned)rows, 256, 0, S(stream)>>>(in, ws, out, H, W, Ho, Wo, C);
   return check_launch("x3d_stem_convs_fwd");
 }
 
@@ -687,8 +706,11 @@ int x3d_stem_convs_wgrad(const float* in, const float* ds, double* dws, int N, i
 
 int x3d_tconv_fwd(const float* in, const float* wt, float* out, int N, int T, int64_t P, int C, int kt, int flip, void* stream) {
   X3D_REQUIRE(in && wt && out && N > 0 && T > 0 && P > 0 && C > 0 && kt > 0 && kt <= 8 && (kt & 1), X3D_ERR_INVALID_ARG, "x3d_tconv_fwd: bad argument");
-  const long total = (long)N * T * P * C;
-  tconv_fwd_kernel<<<ew_blocks(total), 256, 0, S(stream)>>>(in, wt, out, T, P, C, kt, flip, total);
+  X3D_REQUIRE(C % 4 == 0, X3D_ERR_UNSUPPORTED, "x3d_tconv_fwd: C=%d must be a multiple of 4", C);
+  long bx = (P * (C / 4) + 255) / 256;
+  if (bx > 64) bx = 64;
+  X3D_REQUIRE((long)N * T * bx <= 2147483647L, X3D_ERR_UNSUPPORTED, "x3d_tconv_fwd: too many frames");
+  tconv_fwd_kernel<<<(unsigned)((long)N * T * bx), 256, 0, S(stream)>>>(in, wt, out, T, P, C, kt, flip, (int)bx);
   return check_launch("x3d_tconv_fwd");
 }
 
