@@ -73,31 +73,65 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long M, int 
   if (mov_var) mov_var[c] = momentum * mov_var[c] + (1.f - momentum) * (float)v;
 }
 
-// y = (x - mean) * rstd * gamma + beta  (+ ReLU)
+// y = (x - mean) * rstd * gamma + beta  (+ ReLU).  128-bit accesses; the per-channel scale/shift of
+// a thread's 4 channels are combined once (the grid stride is a multiple of C/4 float4 columns, so a
+// thread stays on the same channels) -- no 64-bit modulo and 4 table reads per element.
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
-                long total, int C, int relu) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    float v = (x[i] - mean[c]) * rstd[c] * gamma[c] + beta[c];
-    if (relu) v = fmaxf(v, 0.f);
-    y[i] = v;
+                long total4, int C4, long stride4, int relu) {
+  const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= total4 || i0 >= stride4) return;
+  const int c = (int)(i0 % C4) << 2;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = rstd[c + j] * gamma[c + j];
+    sh[j] = beta[c + j] - mean[c + j] * sc[j];
+  }
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float4* y4 = reinterpret_cast<float4*>(y);
+  for (long i = i0; i < total4; i += stride4) {
+    const float4 v = __ldg(x4 + i);
+    float4 r = make_float4(fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3]));
+    if (relu) r = make_float4(fmaxf(r.x, 0.f), fmaxf(r.y, 0.f), fmaxf(r.z, 0.f), fmaxf(r.w, 0.f));
+    y4[i] = r;
   }
 }
 
-// dx = gamma * rstd * (g - sum_g/M - xhat * sum_gx/M),  g = dy masked by relu_out > 0
+// dx = gamma * rstd * (g - sum_g/M - xhat * sum_gx/M),  g = dy masked by relu_out > 0; same layout.
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ relu_out,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                    const double* __restrict__ sums, float* __restrict__ dx, long total, int C, long M) {
+                    const double* __restrict__ sums, float* __restrict__ dx, long total4, int C4, long stride4, long M) {
+  const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= total4 || i0 >= stride4) return;
+  const int C = C4 << 2, c = (int)(i0 % C4) << 2;
   const double invM = 1.0 / (double)M;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const float g = (relu_out == nullptr || relu_out[i] > 0.f) ? dy[i] : 0.f;
-    const float xh = (x[i] - mean[c]) * rstd[c];
-    const float sg = (float)(sums[c] * invM), sgx = (float)(sums[C + c] * invM);
-    dx[i] = gamma[c] * rstd[c] * (g - sg - xh * sgx);
+  float mu[4], rs[4], k[4], sg[4], sgx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mu[j] = mean[c + j]; rs[j] = rstd[c + j]; k[j] = gamma[c + j] * rs[j];
+    sg[j] = (float)(sums[c + j] * invM); sgx[j] = (float)(sums[C + c + j] * invM);
+  }
+  const float4* dy4 = reinterpret_cast<const float4*>(dy);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const float4* r4 = reinterpret_cast<const float4*>(relu_out);
+  float4* dx4 = reinterpret_cast<float4*>(dx);
+  for (long i = i0; i < total4; i += stride4) {
+    const float4 gv = __ldg(dy4 + i), xv = __ldg(x4 + i);
+    float g[4] = {gv.x, gv.y, gv.z, gv.w};
+    const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+    if (r4 != nullptr) {
+      const float4 rv = __ldg(r4 + i);
+      const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] = rr[j] > 0.f ? g[j] : 0.f;
+    }
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = k[j] * (g[j] - sg[j] - (xx[j] - mu[j]) * rs[j] * sgx[j]);
+    dx4[i] = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -618,17 +652,35 @@ int x3d_bn_finalize(const double* sums, int64_t M, int C, float eps, float momen
   return check_launch("x3d_bn_finalize");
 }
 
+// Grid whose total thread count is a multiple of C/4, so that thread i always sees channel group
+// i mod (C/4) when it strides through the [M, C/4] float4 matrix.
+struct BnGrid { unsigned blocks; long total4, stride4; };
+static BnGrid bn_grid(long M, int C) {
+  const long C4 = C / 4, total4 = M * C4;
+  long threads = 148L * 8 * 256;                       // ~8 CTAs per SM
+  if (threads > total4) threads = total4;
+  threads = (threads + C4 - 1) / C4 * C4;              // multiple of C4 ...
+  long blocks = (threads + 255) / 256;
+  // ... and of 256 where possible: stride = the multiple of C4 actually covered by `blocks` blocks
+  const long stride4 = blocks * 256 / C4 * C4;         // threads >= stride4 never start (i0 check below)
+  return BnGrid{(unsigned)blocks, total4, stride4 > 0 ? stride4 : C4};
+}
+
 int x3d_bn_apply_fwd(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                      float* y, int64_t M, int C, int relu, void* stream) {
   X3D_REQUIRE(x && mean && rstd && gamma && beta && y && M > 0 && C > 0, X3D_ERR_INVALID_ARG, "x3d_bn_apply_fwd: bad argument");
-  bn_apply_kernel<<<ew_blocks(M * C), 256, 0, S(stream)>>>(x, mean, rstd, gamma, beta, y, M * C, C, relu);
+  X3D_REQUIRE(C % 4 == 0, X3D_ERR_UNSUPPORTED, "x3d_bn_apply_fwd: C=%d must be a multiple of 4", C);
+  const BnGrid g = bn_grid(M, C);
+  bn_apply_kernel<<<g.blocks, 256, 0, S(stream)>>>(x, mean, rstd, gamma, beta, y, g.total4, C / 4, g.stride4, relu);
   return check_launch("x3d_bn_apply_fwd");
 }
 
 int x3d_bn_bwd_apply(const float* dy, const float* x, const float* relu_out, const float* mean, const float* rstd,
                      const float* gamma, const double* sums, float* dx, int64_t M, int C, void* stream) {
   X3D_REQUIRE(dy && x && mean && rstd && gamma && sums && dx && M > 0 && C > 0, X3D_ERR_INVALID_ARG, "x3d_bn_bwd_apply: bad argument");
-  bn_bwd_apply_kernel<<<ew_blocks(M * C), 256, 0, S(stream)>>>(dy, x, relu_out, mean, rstd, gamma, sums, dx, M * C, C, M);
+  X3D_REQUIRE(C % 4 == 0, X3D_ERR_UNSUPPORTED, "x3d_bn_bwd_apply: C=%d must be a multiple of 4", C);
+  const BnGrid g = bn_grid(M, C);
+  bn_bwd_apply_kernel<<<g.blocks, 256, 0, S(stream)>>>(dy, x, relu_out, mean, rstd, gamma, sums, dx, g.total4, C / 4, g.stride4, M);
   return check_launch("x3d_bn_bwd_apply");
 }
 
