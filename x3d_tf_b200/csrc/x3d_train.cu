@@ -480,11 +480,24 @@ __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); 
 // out = swish(y * s[n, c])   (s == nullptr: factor 1)      model.py:311-316
 __global__ void __launch_bounds__(256)
 scale_swish_fwd_kernel(const float* __restrict__ y, const float* __restrict__ s, float* __restrict__ out,
-                       long total, int C, long rows_per_clip) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const float v = s ? y[i] * s[(i / C / rows_per_clip) * C + c] : y[i];
-    out[i] = v * sigm(v);
+                       long clip4, int C4, long stride4) {
+  // blockIdx.y = clip; 128-bit accesses; the thread stride is a multiple of C/4, so a thread keeps its
+  // 4 channels (and their SE factors) for the whole clip
+  const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= clip4 || i0 >= stride4) return;
+  const long n = blockIdx.y;
+  const int c = (int)(i0 % C4) << 2;
+  float sc[4] = {1.f, 1.f, 1.f, 1.f};
+  if (s) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sc[j] = s[n * (C4 << 2) + c + j];
+  }
+  const float4* y4 = reinterpret_cast<const float4*>(y) + n * clip4;
+  float4* o4 = reinterpret_cast<float4*>(out) + n * clip4;
+  for (long i = i0; i < clip4; i += stride4) {
+    const float4 v = __ldg(y4 + i);
+    const float a[4] = {v.x * sc[0], v.y * sc[1], v.z * sc[2], v.w * sc[3]};
+    o4[i] = make_float4(a[0] * sigm(a[0]), a[1] * sigm(a[1]), a[2] * sigm(a[2]), a[3] * sigm(a[3]));
   }
 }
 // dv = dout * (sig(v) * (1 + v * (1 - sig(v))));  dy = dv * s;  ds[n,c] += sum_p dv * y
@@ -779,7 +792,17 @@ int x3d_tconv_wgrad(const float* s, const float* dy, double* dwt, int N, int T, 
 
 int x3d_scale_swish_fwd(const float* y, const float* s, float* out, int64_t M, int C, int64_t rows_per_clip, void* stream) {
   X3D_REQUIRE(y && out && M > 0 && C > 0 && rows_per_clip > 0, X3D_ERR_INVALID_ARG, "x3d_scale_swish_fwd: bad argument");
-  scale_swish_fwd_kernel<<<ew_blocks(M * C), 256, 0, S(stream)>>>(y, s, out, M * C, C, rows_per_clip);
+  X3D_REQUIRE(C % 4 == 0 && M % rows_per_clip == 0 && M / rows_per_clip <= 65535, X3D_ERR_UNSUPPORTED,
+              "x3d_scale_swish_fwd: C=%d must be a multiple of 4, M a multiple of rows_per_clip, <= 65535 clips", C);
+  const long clips = M / rows_per_clip, C4 = C / 4, clip4 = rows_per_clip * C4;
+  long threads = 148L * 8 * 256 / clips;                // ~8 CTAs per SM over all clips
+  if (threads < 256) threads = 256;
+  if (threads > clip4) threads = clip4;
+  const long blocks = (threads + 255) / 256;
+  long stride4 = blocks * 256 / C4 * C4;
+  if (stride4 <= 0) stride4 = C4;
+  dim3 grid((unsigned)blocks, (unsigned)clips);
+  scale_swish_fwd_kernel<<<grid, 256, 0, S(stream)>>>(y, s, out, clip4, (int)C4, stride4);
   return check_launch("x3d_scale_swish_fwd");
 }
 
