@@ -183,3 +183,36 @@ def test_predict_pipelined_host_batches_equal_call():
     assert list(m.predict([])) == []
     with pytest.raises(ValueError):
         list(m.predict([odd[:1]]))
+
+
+@pytest.mark.parametrize("variant,T,S,views,clips", [("X3D_M", 16, 256, 10, 20),      # BASELINE configs[2]
+                                                     ("X3D_S", 13, 182, 3, 6),        # configs[1] shape, 3-crop
+                                                     ("X3D_L", 16, 356, 1, 3)])       # configs[3] shape
+def test_full_size_properties(variant, T, S, views, clips):
+    """At BASELINE.json's full clip sizes (where the fp64 oracle is only affordable for one clip):
+    one clip against the oracle, then size-independent properties for the whole batch -- a clip's
+    logits do not depend on the batch it is in, the video probabilities are the mean of its views'
+    softmaxes, rows sum to one, and the graph replay reproduces the eager launches bit for bit."""
+    m, cfg, W, spec = _model(variant, dtype="bfloat16", views=views)
+    x = synthetic_clips(clips, T, S, S, cfg.DATA.MEAN, cfg.DATA.STD, seed=21)
+    xd = to_dev(x, torch.bfloat16)
+    probs = m(xd).clone()
+    logits = m.last_logits.clone()
+    assert torch.isfinite(logits).all() and probs.shape == (clips // views, cfg.NETWORK.NUM_CLASSES)
+    # (1) one full-size clip against the float64 oracle
+    spec1 = O.OracleSpec.from_cfg(cfg)
+    spec1.num_preds = 1
+    want = O.forward(W, spec1, x[:1], torch.float64)["logits"]
+    err = rel_err(to_np(logits[:1]), want)
+    assert err < BF16_TOL, err
+    # (2) batch independence: the last `views` clips alone
+    m(xd[-views:].contiguous())
+    assert torch.equal(m.last_logits, logits[-views:])
+    # (3) view mean and normalisation
+    ref = torch.softmax(logits.float(), -1).reshape(clips // views, views, -1).mean(1)
+    np.testing.assert_allclose(to_np(probs), to_np(ref), rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(to_np(probs).sum(-1), 1.0, rtol=1e-4)
+    # (4) CUDA-graph replay == eager
+    mg, *_ = _model(variant, dtype="bfloat16", views=views, graph=True)
+    mg(xd); mg(xd)
+    assert torch.equal(mg.last_logits, logits)
