@@ -254,6 +254,10 @@ int x3d_softmax_xent(const float* logits, const int32_t* labels, float* loss, fl
 /* SGD(nesterov=True) + L2, train.py:88-92, model.py:47:  g = grad + wd*w; v = mu*v - lr*g; w += mu*v - lr*g */
 int x3d_sgd_nesterov_step(float* w, const float* grad, float* v, const float* wd, int64_t n,
                           float lr, float momentum, void* stream);
+/* Adam, train.py:93-95 (Keras defaults):  g = grad + wd*w; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ * w -= lr_t m / (sqrt(v) + eps), with lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) passed by the caller. */
+int x3d_adam_step(float* w, const float* grad, float* m, float* v, const float* wd, int64_t n,
+                  float lr_t, float beta1, float beta2, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -113,10 +113,14 @@ def train_step(W: Dict[str, np.ndarray], spec: O.OracleSpec, clips: np.ndarray, 
                *, lr: float, momentum: float = 0.9, weight_decay: float = 5e-5,
                bn_momentum: float = 0.9, velocity: Optional[Dict[str, np.ndarray]] = None,
                dropout_mask: Optional[np.ndarray] = None, world: int = 1, dtype=torch.float64,
-               taps: Optional[dict] = None, relu_masks: Optional[list] = None):
+               taps: Optional[dict] = None, relu_masks: Optional[list] = None,
+               optimizer: str = "sgd", adam_state: Optional[dict] = None):
     """One replica's step.  `world` > 1 scales the data loss by 1/world as Keras does under
     MirroredStrategy (gradients are then summed across replicas by the caller).
-    Returns dict(loss, grads, weights, velocity, logits)."""
+    `optimizer="adam"` applies Keras' Adam instead (train.py:93-95; tensorflow==2.4.1
+    `optimizer_v2/adam.py`: beta_1 0.9, beta_2 0.999, epsilon 1e-7, lr_t = lr sqrt(1-b2^t)/(1-b1^t));
+    `adam_state` = dict(t=steps done, m={...}, v={...}).
+    Returns dict(loss, grads, weights, velocity, logits[, adam_v])."""
     P = {}
     for k, v in W.items():
         t = torch.from_numpy(np.ascontiguousarray(v)).to(dtype)
@@ -135,9 +139,20 @@ def train_step(W: Dict[str, np.ndarray], spec: O.OracleSpec, clips: np.ndarray, 
     names = [k for k in P if P[k].requires_grad]
     grads = torch.autograd.grad(loss, [P[k] for k in names])   # retain_grad() hooks of `taps` fire here too
     G = {k: g.detach().numpy() for k, g in zip(names, grads)}
-    newW, newV = {}, {}
+    newW, newV, newV2 = {}, {}, {}
     for k in W:
-        if k in G:
+        if k in G and optimizer == "adam":
+            b1, b2, eps = 0.9, 0.999, 1e-7
+            st = adam_state or {"t": 0, "m": {}, "v": {}}
+            t = st["t"] + 1
+            m0 = st["m"].get(k, np.zeros_like(G[k])).astype(np.float64)
+            s0 = st["v"].get(k, np.zeros_like(G[k])).astype(np.float64)
+            m1 = b1 * m0 + (1 - b1) * G[k]
+            s1 = b2 * s0 + (1 - b2) * G[k] ** 2
+            lr_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+            newV[k], newV2[k] = m1, s1
+            newW[k] = W[k].astype(np.float64) - lr_t * m1 / (np.sqrt(s1) + eps)
+        elif k in G:
             v0 = np.zeros_like(G[k]) if velocity is None else velocity[k].astype(np.float64)
             v1 = momentum * v0 - lr * G[k]
             newV[k] = v1
@@ -150,4 +165,4 @@ def train_step(W: Dict[str, np.ndarray], spec: O.OracleSpec, clips: np.ndarray, 
         newW[prefix + "/moving_variance"] = bn_momentum * W[prefix + "/moving_variance"].astype(np.float64) + \
             (1 - bn_momentum) * var.numpy()
     return {"loss": float(data_loss.detach() * world), "grads": G, "weights": newW, "velocity": newV,
-            "logits": logits.detach().numpy()}
+            "adam_v": newV2, "logits": logits.detach().numpy()}

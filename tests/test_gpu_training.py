@@ -178,3 +178,53 @@ def test_train_driver_epochs_checkpoints_and_resume(tmp_path, capsys):
     r2 = T.run(args + ["--epochs", "3"])                                   # resumes at epoch 2, runs epoch 3 only
     assert [h["epoch"] for h in r2["history"]] == [3] and r2["iteration"] == 6
     assert "Found checkpoint" in capsys.readouterr().err
+
+
+def test_adam_step_matches_oracle(tmp_path):
+    """cfg.TRAIN.OPTIMIZER = 'adam' (train.py:93-95): two Adam steps against the float64 oracle's
+    Keras-Adam update (step 2 is evaluated at the CUDA run's own step-1 state, as for SGD), and the
+    `m` / `v` slots survive a checkpoint round trip.
+
+    Adam's step is lr * m / (sqrt(v) + eps): where a gradient is within fp32 noise of zero the
+    direction is undetermined, so the comparison is the L2 distance of each tensor's displacement
+    (5e-2), not an element-wise bound."""
+    from x3d_tf_b200.arch import build_arch
+    from x3d_tf_b200.config import get_config
+    from x3d_tf_b200.synth import synthetic_clips, synthetic_weights
+    from x3d_tf_b200.training import X3DTrainer
+    cfg = get_config("X3D_XS", freeze=False)
+    cfg.NETWORK.DROPOUT_RATE = 0.0
+    cfg.TRAIN.OPTIMIZER = "adam"
+    cfg.freeze()
+    W = synthetic_weights(build_arch(cfg), seed=3)
+    x = synthetic_clips(2, 4, 64, 64, cfg.DATA.MEAN, cfg.DATA.STD, seed=4)
+    labels = np.random.default_rng(5).integers(0, 400, size=2).astype(np.int32)
+    spec = O.OracleSpec.from_cfg(cfg)
+    wd = float(cfg.NETWORK.WEIGHT_DECAY)
+    tr = X3DTrainer(cfg).load(W)
+    assert tr.optimizer == "adam"
+    xd, ld = torch.from_numpy(x).cuda(), torch.from_numpy(labels).cuda()
+    state, Wprev = None, W
+    for step, lr in enumerate((1e-3, 5e-4)):
+        tr.relu_masks = []
+        tr.step(xd, ld, lr)
+        torch.cuda.synchronize()
+        ref = TO.train_step(Wprev, spec, x, labels, lr=lr, weight_decay=wd, relu_masks=tr.relu_masks,
+                            optimizer="adam", adam_state=state)
+        Wn = tr.weights()
+        bad = []
+        for k, v in ref["weights"].items():
+            if k.endswith("moving_mean") or k.endswith("moving_variance"):
+                continue
+            e = _l2(Wn[k].astype(np.float64) - Wprev[k], v - Wprev[k])
+            if e > 5e-2:
+                bad.append((k, e))
+        assert not bad, (step, bad[:10])
+        state = {"t": step + 1, "m": tr.velocity(), "v": tr.second_moment()}      # continue from the CUDA state
+        Wprev = Wn
+    prefix = str(tmp_path / "ckpt-1")
+    tr.save_checkpoint(prefix, lr=5e-4)
+    tr2 = X3DTrainer(cfg)
+    st = tr2.load_checkpoint(prefix, strict_slots=True)
+    assert st["iter"] == 2 and abs(st["beta_2"] - 0.999) < 1e-6
+    assert torch.equal(tr2.v, tr.v) and torch.equal(tr2.v2, tr.v2) and torch.equal(tr2.w, tr.w)

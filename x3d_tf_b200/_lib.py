@@ -88,6 +88,7 @@ SIGNATURES = {
     "x3d_strided_add": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 7 + [C.c_void_p]),
     "x3d_dropout_mask": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_uint64, C.c_void_p]),
     "x3d_softmax_xent": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "x3d_adam_step": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "x3d_sgd_nesterov_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_float, C.c_float, C.c_void_p]),
     # ---- either side of the path: input stage and evaluation metrics
     "x3d_normalize_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_float),

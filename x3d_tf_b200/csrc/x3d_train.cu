@@ -631,6 +631,22 @@ sgd_nesterov_kernel(float* __restrict__ w, const float* __restrict__ grad, float
   }
 }
 
+// Adam as Keras applies it (train.py:93-95; tf.optimizers.Adam defaults beta_1 0.9, beta_2 0.999,
+// epsilon 1e-7):  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  w -= lr_t m / (sqrt(v) + eps),
+// lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) computed by the caller;  g = grad + wd[i] w as for SGD.
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ w, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
+            const float* __restrict__ wd, long n, float lr_t, float b1, float b2, float eps) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float g = grad[i] + wd[i] * w[i];
+    const float mn = b1 * m[i] + (1.f - b1) * g;
+    const float vn = b2 * v[i] + (1.f - b2) * g * g;
+    m[i] = mn;
+    v[i] = vn;
+    w[i] = w[i] - lr_t * mn / (sqrtf(vn) + eps);
+  }
+}
+
 static inline unsigned ew_blocks(long n) {
   long b = (n + 255) / 256;
   if (b > 148L * 32) b = 148L * 32;
@@ -848,6 +864,13 @@ int x3d_softmax_xent(const float* logits, const int32_t* labels, float* loss, fl
   X3D_REQUIRE(logits && labels && loss && dlogits && N > 0 && ncls > 0, X3D_ERR_INVALID_ARG, "x3d_softmax_xent: bad argument");
   softmax_xent_kernel<<<N, 256, 0, S(stream)>>>(logits, labels, loss, dlogits, ncls, gscale);
   return check_launch("x3d_softmax_xent");
+}
+
+int x3d_adam_step(float* w, const float* grad, float* m, float* v, const float* wd, int64_t n, float lr_t,
+                  float beta1, float beta2, float eps, void* stream) {
+  X3D_REQUIRE(w && grad && m && v && wd && n > 0, X3D_ERR_INVALID_ARG, "x3d_adam_step: bad argument");
+  adam_kernel<<<ew_blocks(n), 256, 0, S(stream)>>>(w, grad, m, v, wd, n, lr_t, beta1, beta2, eps);
+  return check_launch("x3d_adam_step");
 }
 
 int x3d_sgd_nesterov_step(float* w, const float* grad, float* v, const float* wd, int64_t n, float lr, float momentum,

@@ -346,6 +346,7 @@ def load_model_variables(prefix: str, verify: bool = True,
 
 
 SLOT_INFIX = "/.OPTIMIZER_SLOT/optimizer/momentum"
+SLOT_M, SLOT_V = "/.OPTIMIZER_SLOT/optimizer/m", "/.OPTIMIZER_SLOT/optimizer/v"       # Adam
 
 
 def load_optimizer_state(prefix: str, verify: bool = True) -> Dict[str, object]:
@@ -355,7 +356,8 @@ def load_optimizer_state(prefix: str, verify: bool = True) -> Dict[str, object]:
     {"iter": int, "learning_rate": float|None, "momentum": float|None, "decay": float|None,
      "slots": {variable path -> float32 array}}; missing pieces are None / empty."""
     rd = BundleReader(prefix)
-    out: Dict[str, object] = {"iter": None, "learning_rate": None, "momentum": None, "decay": None, "slots": {}}
+    out: Dict[str, object] = {"iter": None, "learning_rate": None, "momentum": None, "decay": None,
+                              "beta_1": None, "beta_2": None, "slots": {}, "slots_m": {}, "slots_v": {}}
     for k in rd.keys():
         if not k.endswith(VAR_SUFFIX):
             continue
@@ -369,6 +371,28 @@ def load_optimizer_state(prefix: str, verify: bool = True) -> Dict[str, object]:
                 out[field] = float(np.asarray(v).reshape(-1)[0])
         elif name.endswith(SLOT_INFIX):
             out["slots"][name[:-len(SLOT_INFIX)]] = rd.tensor(k, verify)
+        elif name.endswith(SLOT_M):
+            out["slots_m"][name[:-len(SLOT_M)]] = rd.tensor(k, verify)
+        elif name.endswith(SLOT_V):
+            out["slots_v"][name[:-len(SLOT_V)]] = rd.tensor(k, verify)
+    return out
+
+
+def adam_tensors(iteration: int, learning_rate: float, beta_1: float, beta_2: float,
+                 m: Dict[str, np.ndarray], v: Dict[str, np.ndarray], decay: float = 0.0) -> Dict[str, np.ndarray]:
+    """Keras Adam's checkpoint entries: `optimizer/{iter,learning_rate,beta_1,beta_2,decay}` and the
+    `m` / `v` slots of every trainable variable."""
+    out: Dict[str, np.ndarray] = {
+        "optimizer/iter": np.asarray(iteration, np.int64),
+        "optimizer/learning_rate": np.asarray(learning_rate, np.float32),
+        "optimizer/beta_1": np.asarray(beta_1, np.float32),
+        "optimizer/beta_2": np.asarray(beta_2, np.float32),
+        "optimizer/decay": np.asarray(decay, np.float32),
+    }
+    for name, a in m.items():
+        out[name + SLOT_M] = np.asarray(a, np.float32)
+    for name, a in v.items():
+        out[name + SLOT_V] = np.asarray(a, np.float32)
     return out
 
 

@@ -89,8 +89,8 @@ def run(argv: Optional[List[str]] = None) -> Optional[dict]:
         cfg = get_default_config(); cfg.merge_from_file(a.config); cfg.freeze()
     else:
         cfg = get_config(a.config)
-    if cfg.TRAIN.OPTIMIZER.lower() != "sgd":
-        raise NotImplementedError(f"{cfg.TRAIN.OPTIMIZER} not supported")          # train.py:97 (adam: not built)
+    if cfg.TRAIN.OPTIMIZER.lower() not in ("sgd", "adam"):
+        raise NotImplementedError(f"{cfg.TRAIN.OPTIMIZER} not supported")          # train.py:96-97
     os.makedirs(a.model_dir, exist_ok=True)
 
     import torch.distributed as dist

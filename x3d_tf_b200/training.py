@@ -66,6 +66,11 @@ class X3DTrainer:
         self.wd2 = 2.0 * float(net.WEIGHT_DECAY)
         self.dropout = float(net.DROPOUT_RATE)
         self.momentum = float(cfg.TRAIN.MOMENTUM) if hasattr(cfg, "TRAIN") and hasattr(cfg.TRAIN, "MOMENTUM") else 0.9
+        # train.py:85-97: 'sgd' (Nesterov momentum) or 'adam' (Keras defaults)
+        self.optimizer = str(cfg.TRAIN.OPTIMIZER).lower() if hasattr(cfg, "TRAIN") and hasattr(cfg.TRAIN, "OPTIMIZER") else "sgd"
+        if self.optimizer not in ("sgd", "adam"):
+            raise NotImplementedError(f"{self.optimizer} not supported")
+        self.adam = (0.9, 0.999, 1e-7)
         self.seed, self.iteration = seed, 0
         self.fixed_dropout_mask: Optional[torch.Tensor] = None      # tests inject a mask
         self.relu_masks: Optional[list] = None                      # tests: record every ReLU's sign pattern
@@ -117,7 +122,8 @@ class X3DTrainer:
         self.w = torch.zeros(n, dtype=torch.float32, device=dev)
         self.g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.g64 = torch.zeros(n, dtype=torch.float64, device=dev)
-        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)          # SGD momentum / Adam m
+        self.v2 = torch.zeros(n, dtype=torch.float32, device=dev) if self.optimizer == "adam" else None   # Adam v
         self.wd = torch.zeros(n, dtype=torch.float32, device=dev)
         for name in self.layout.slots:
             if self.decay[name]:
@@ -179,8 +185,13 @@ class X3DTrainer:
         return {n: self._from_dev_layout(n, self.layout.view(self.g, n)) for n in self.layout.slots}
 
     def velocity(self) -> Dict[str, np.ndarray]:
-        """Momentum slots (the `.OPTIMIZER_SLOT/optimizer/momentum` variables of a Keras checkpoint)."""
+        """Momentum slots (the `.OPTIMIZER_SLOT/optimizer/momentum` variables of a Keras checkpoint;
+        Adam: the first-moment slots `.../optimizer/m`)."""
         return {n: self._from_dev_layout(n, self.layout.view(self.v, n)) for n in self.layout.slots}
+
+    def second_moment(self) -> Dict[str, np.ndarray]:
+        """Adam's `.OPTIMIZER_SLOT/optimizer/v` slots."""
+        return {n: self._from_dev_layout(n, self.layout.view(self.v2, n)) for n in self.layout.slots}
 
     # ------------------------------------------------------------------ checkpoints (utils.py:128-132)
     def save_checkpoint(self, prefix: str, lr: float = 0.0) -> None:
@@ -190,7 +201,11 @@ class X3DTrainer:
         `checkpoint` state file.  (No object graph: readable by name, see tf_bundle.write_bundle.)"""
         from . import tf_bundle
         tensors = dict(self.weights())
-        tensors.update(tf_bundle.optimizer_tensors(self.iteration, lr, self.momentum, self.velocity()))
+        if self.optimizer == "adam":
+            tensors.update(tf_bundle.adam_tensors(self.iteration, lr, self.adam[0], self.adam[1],
+                                                  self.velocity(), self.second_moment()))
+        else:
+            tensors.update(tf_bundle.optimizer_tensors(self.iteration, lr, self.momentum, self.velocity()))
         tf_bundle.write_bundle(prefix, tensors)
 
     def load_checkpoint(self, prefix: str, strict_slots: bool = False) -> dict:
@@ -201,13 +216,19 @@ class X3DTrainer:
         from . import tf_bundle
         self.load(tf_bundle.load_model_variables(prefix))
         st = tf_bundle.load_optimizer_state(prefix)
-        slots = st["slots"]
+        adam = self.optimizer == "adam"
+        slots = st["slots_m"] if adam else st["slots"]
         self.v.zero_()
+        if adam:
+            self.v2.zero_()
         for name in self.layout.slots:
             if name in slots:
                 self.layout.view(self.v, name).copy_(torch.from_numpy(self._to_dev_layout(name, slots[name])))
+                if adam and name in st["slots_v"]:
+                    self.layout.view(self.v2, name).copy_(
+                        torch.from_numpy(self._to_dev_layout(name, st["slots_v"][name])))
             elif strict_slots:
-                raise KeyError(f"{prefix}: no momentum slot for {name}")
+                raise KeyError(f"{prefix}: no optimizer slot for {name}")
         if st["iter"] is not None:
             self.iteration = int(st["iter"])
         return st
@@ -493,9 +514,16 @@ class X3DTrainer:
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.g, op=dist.ReduceOp.SUM, group=self.pg)
-        check(lib().x3d_sgd_nesterov_step(self.w.data_ptr(), self.g.data_ptr(), self.v.data_ptr(),
-                                          self.wd.data_ptr(), n, float(lr), self.momentum, _s()),
-              "x3d_sgd_nesterov_step")
+        if self.optimizer == "adam":
+            b1, b2, eps = self.adam
+            t = self.iteration + 1
+            lr_t = float(lr) * (1.0 - b2 ** t) ** 0.5 / (1.0 - b1 ** t)
+            check(lib().x3d_adam_step(self.w.data_ptr(), self.g.data_ptr(), self.v.data_ptr(), self.v2.data_ptr(),
+                                      self.wd.data_ptr(), n, lr_t, b1, b2, eps, _s()), "x3d_adam_step")
+        else:
+            check(lib().x3d_sgd_nesterov_step(self.w.data_ptr(), self.g.data_ptr(), self.v.data_ptr(),
+                                              self.wd.data_ptr(), n, float(lr), self.momentum, _s()),
+                  "x3d_sgd_nesterov_step")
         self.iteration += 1
         return loss
 
