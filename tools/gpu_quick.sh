@@ -1,4 +1,11 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
-timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_model.py -m gpu -q -p no:cacheprovider -x -k "tcgen05 or tc_path or bf16 or full_size" 2>&1 | tail -4
-timeout 600 python tools/prof_layers.py pw --size 256 --clips 80 --reps 5 2>&1
+mkdir -p gpurun_out
+for v in 0 1 0 1; do
+X3D_SWISH_IN_DW=$v timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 > gpurun_out/bench_q.txt
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_q.txt').read().strip().splitlines()[-1])
+print('swish_in_dw=$v', round(d['value'],1), round(d['ms_per_step'],3), {k:(v['ms'] if isinstance(v,dict) and 'ms' in v else v) for k,v in d['kernel_classes'].items() if k in ('a','b','c')})
+PY
+done

@@ -25,6 +25,17 @@ namespace tc {
 constexpr int kBlockM = 128, kBlockK = 64, kStageBytes = kBlockM * kBlockK * 2;
 using namespace ptx;
 
+// Timeline trace of one epilogue group (diagnostics only: nvcc -DX3D_PW_TRACE; tools/trace_pw.py).
+#ifdef X3D_PW_TRACE
+__device__ long long g_pw_trace[8 * 256];
+#define X3D_TRACE(slot)                                                                  \
+  do {                                                                                   \
+    if (trace_on && trace_n < 256) g_pw_trace[trace_n * 8 + (slot)] = clock64();         \
+  } while (0)
+#else
+#define X3D_TRACE(slot) do {} while (0)
+#endif
+
 __device__ __forceinline__ void tcgen05_before_sync() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -216,8 +227,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                            static_cast<uint32_t>(grp * p.NT);
     uint32_t sub_ctr = 0, aph = 0;
+#ifdef X3D_PW_TRACE
+    const bool trace_on = blockIdx.x == 7 && blockIdx.y == 0 && grp == 0 && leader;
+    int trace_n = 0;
+#endif
     for (long tile = blockIdx.x + static_cast<long>(grp) * gridDim.x; tile < num_tiles;
          tile += 2L * gridDim.x, aph ^= 1) {
+      X3D_TRACE(0);
       const long row = tile * kBlockM + r_loc;
       const bool row_ok = row < p.M;
       const bf16* rrow = (p.R && row_ok) ? p.R + row * p.ldr + n0 : nullptr;
@@ -227,7 +243,18 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int c = 0; c < 8; ++c)
         rr[c] = (rrow && c * 8 < p.NT && n0 + c * 8 < p.Nc) ? __ldg(reinterpret_cast<const uint4*>(rrow + c * 8))
                                                            : make_uint4(0, 0, 0, 0);
+      // The residual rows come from DRAM (several kernels ago) and their latency is exposed in the
+      // drain below (timeline: tools/trace_pw.py): pull the NEXT tile's rows of this group into L2 now
+      if (p.R) {
+        const long nrow = row + 2L * gridDim.x * kBlockM;
+        if (nrow < p.M) {
+          const char* np_ = reinterpret_cast<const char*>(p.R + nrow * p.ldr + n0);
+          for (int off = 0; off < p.NT * 2; off += 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + off));
+        }
+      }
       mbar_wait(&t_full[grp], aph);
+      X3D_TRACE(1);
       tcgen05_after_sync();
       for (int sb = 0; sb < n_sub; ++sb, ++sub_ctr) {
         if (n0 + sb * 64 >= p.Nc) break;          // uniform across the CTA
@@ -247,6 +274,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
+#ifdef X3D_PW_TRACE
+          if (g == 0 && sb == 0 && trace_on && trace_n < 256) g_pw_trace[trace_n * 8 + 7] = clock64();
+#endif
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int cc = c0 + h * 8;
@@ -278,22 +308,30 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                          "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
           }
         }
+        X3D_TRACE(2);
         if (sb == n_sub - 1 || n0 + (sb + 1) * 64 >= p.Nc) {
           tcgen05_before_sync();                  // last TMEM read of this tile is done
           mbar_arrive(&t_empty[grp]);
         }
         fence_proxy_async();
+        X3D_TRACE(3);
         // the store issued after the previous barrier has (long since) finished reading its
         // staging buffer: checked here, off the critical path, so that buffer is free again for
         // everybody once this barrier is passed
         if (leader) tma_store_wait_read<0>();
+        X3D_TRACE(4);
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
+        X3D_TRACE(5);
         if (leader) {
           tma_store_2d(&tmD, stage0 + (sub_ctr & 1) * kStageBytes, n0 + sb * 64,
                        static_cast<int>(tile * kBlockM));
           tma_store_commit();
         }
+        X3D_TRACE(6);
+#ifdef X3D_PW_TRACE
+        if (trace_on) ++trace_n;
+#endif
       }
     }
     if (leader) tma_store_wait_read<0>();
@@ -487,3 +525,9 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   }
   return check_launch("x3d_pw_tc_fwd");
 }
+
+#ifdef X3D_PW_TRACE
+extern "C" int x3d_pw_trace_dump(long long* host_out) {      // [256][8] clock64 stamps of CTA 7, group 0
+  return cudaMemcpyFromSymbol(host_out, x3d::tc::g_pw_trace, sizeof(long long) * 8 * 256) == cudaSuccess ? 0 : -3;
+}
+#endif

@@ -12,6 +12,8 @@ There is no CPU / PyTorch fallback: without the CUDA library or a GPU, `call` ra
 """
 from __future__ import annotations
 
+import os
+
 import math
 from collections import OrderedDict
 from typing import Dict, Iterable, List, Optional, Tuple
@@ -235,9 +237,11 @@ class Options:
     # "fused" = x3d_stem_tc_u8_fwd (the stem's loader reads bytes through a lookup table)
     stem_u8 = "normalize"
     # blocks without SE: apply swish in the channelwise kernel's epilogue (x3d_dw3x3x3_act_fwd)
-    # instead of the projection GEMM's prologue.  Measured at 80 clips of 16x256^2: c 2.80 -> 2.51 ms
-    # but b 4.93 -> 5.14 ms (the stencil is the FMA/issue-bound kernel), net 0.3 %: off by default.
-    swish_in_dw = False
+    # instead of the projection GEMM's prologue, which then runs without its transform warps.
+    # Measured back to back at 80 clips of 16x256^2: c 2.83 -> 2.50 ms, b 4.97 -> 5.18 ms (the stencil
+    # is the FMA/issue-bound kernel), step 11.91 -> 11.75 ms (+1.4 % clips/s); X3D_SWISH_IN_DW=0 turns
+    # it off.
+    swish_in_dw = os.environ.get("X3D_SWISH_IN_DW", "1") == "1"
 
 
 def _use_tc() -> bool:
