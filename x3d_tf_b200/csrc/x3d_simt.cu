@@ -334,6 +334,161 @@ pw_gemm_kernel(const PwParams p) {
 }
 
 // =====================================================================================
+// fp32 pointwise GEMM on the tensor cores: 3xTF32 split (x = hi + lo, both TF32; a.b ~ lo.hi + hi.lo
+// + hi.hi accumulated in fp32), which keeps fp32-level accuracy (the 1e-4 logit bound of the fp32
+// path and the gradient checks of the training step) at a third of the TF32 rate - still far above
+// the FFMA rate the CUDA-core kernel above is bound by.  Same contract as pw_gemm_kernel<float,
+// float>: 128x64 tile, BK = 16, 256 threads; 8 warps own 32x32 sub-tiles (2x4 m16n8k8 fragments).
+// Two shared-memory stages, the next K slice is fetched into registers while the MMAs run.
+constexpr int kTAPitch = kBK + 4;      // A tile [m][k]: fragment reads (8 rows x 4 k) hit 32 banks
+constexpr int kTWPitch = kBN + 8;      // W tile [k][n]: fragment reads (4 k x 8 n) hit 32 banks
+
+// hi = x rounded to TF32 (half away from zero) with integer ops, lo = x - hi (exact) pre-biased by half a
+// TF32 ulp so that the tensor core's truncation of the low 13 mantissa bits rounds it.  cvt.rna.tf32
+// runs on the 16-lane conversion pipe and made the kernel conversion-bound (measured: 124 MAC/clk/SM).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(256, 2)
+pw_gemm_tf32x3_kernel(const PwParams p) {
+  __shared__ __align__(16) float As[2][kBM][kTAPitch];
+  __shared__ __align__(16) float Ws[2][kBK][kTWPitch];
+  const int tid = threadIdx.x;
+  const long m0 = (long)blockIdx.x * kBM;
+  const int n0 = blockIdx.y * kBN;
+  const float* A = static_cast<const float*>(p.A);
+
+  // loader roles as in pw_gemm_kernel: A row lr / k-half lk, W row wk / 4 columns from wn
+  const int lr = tid >> 1, lk = (tid & 1) * 8;
+  const long lm = m0 + lr;
+  long arow = -1;
+  long clip = 0;
+  if (lm < p.M) {
+    arow = lm;
+    if (p.gather) {
+      long q = lm;
+      const int wo = (int)(q % p.Wo); q /= p.Wo;
+      const int ho = (int)(q % p.Ho); q /= p.Ho;       // q = n*T + t
+      arow = (q * p.Hi + (long)ho * p.stride) * p.Wi + (long)wo * p.stride;
+    }
+    if (p.se) clip = lm / p.rows_per_clip;
+  }
+  const int wk = tid >> 4, wn = (tid & 15) * 4;
+
+  float av[8];
+  float4 wv;
+  auto fetch = [&](int k0) {
+    const int ka = k0 + lk;
+    if (arow >= 0 && ka < p.K) {
+      ld8(A + arow * p.lda + ka, av);
+      if (p.se) {
+        const float* sp = p.se + clip * p.K + ka;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) av[i] *= __ldg(sp + i);
+      }
+      if (p.swish) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) av[i] = av[i] * sigmoidf_<false>(av[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) av[i] = 0.f;
+    }
+    wv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k0 + wk < p.K && n0 + wn < p.Nc)
+      wv = __ldg(reinterpret_cast<const float4*>(p.Wt + (long)(k0 + wk) * p.ldw + n0 + wn));
+  };
+  auto stage = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][lr][lk]) = make_float4(av[0], av[1], av[2], av[3]);
+    *reinterpret_cast<float4*>(&As[buf][lr][lk + 4]) = make_float4(av[4], av[5], av[6], av[7]);
+    *reinterpret_cast<float4*>(&Ws[buf][wk][wn]) = wv;
+  };
+
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = (warp & 3) * 32, wc = (warp >> 2) * 32;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+
+  fetch(0);
+  stage(0);
+  __syncthreads();
+  const int nk = (p.K + kBK - 1) / kBK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) fetch((kt + 1) * kBK);          // in flight while the MMAs below run
+#pragma unroll
+    for (int ks = 0; ks < kBK; ks += 8) {
+      if (kt * kBK + ks >= p.K) break;               // K is a multiple of 8: skip an all-zero half
+      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float* ap = &As[buf][wm + i * 16 + g][ks + t];
+        split_tf32(ap[0], ah[i][0], al[i][0]);
+        split_tf32(ap[8 * kTAPitch], ah[i][1], al[i][1]);
+        split_tf32(ap[4], ah[i][2], al[i][2]);
+        split_tf32(ap[8 * kTAPitch + 4], ah[i][3], al[i][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* bp = &Ws[buf][ks + t][wc + j * 8 + g];
+        split_tf32(bp[0], bh[j][0], bl[j][0]);
+        split_tf32(bp[4 * kTWPitch], bh[j][1], bl[j][1]);
+      }
+      // term-major order: 8 independent MMAs between two that share an accumulator; column
+      // fragments beyond Nc (warp-uniform) are skipped
+#pragma unroll
+      for (int term = 0; term < 3; ++term)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (n0 + wc + j * 8 >= p.Nc) continue;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) mma_tf32(acc[i][j], term == 0 ? al[i] : ah[i], term == 1 ? bl[j] : bh[j]);
+        }
+    }
+    if (kt + 1 < nk) stage(buf ^ 1);                 // last read before the barrier that ended kt-1
+    __syncthreads();
+  }
+
+  float* D = static_cast<float*>(p.D);
+  const float* R = static_cast<const float*>(p.R);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = n0 + wc + j * 8 + 2 * t;         // Nc is a multiple of 4, col is even
+    if (col >= p.Nc) continue;
+    float2 bv = make_float2(0.f, 0.f);
+    if (p.bias) bv = __ldg(reinterpret_cast<const float2*>(p.bias + col));
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long m = m0 + wm + i * 16 + g + h * 8;
+        if (m >= p.M) continue;
+        float2 y = make_float2(acc[i][j][2 * h] + bv.x, acc[i][j][2 * h + 1] + bv.y);
+        if (R) {
+          const float2 rv = __ldg(reinterpret_cast<const float2*>(R + m * p.ldr + col));
+          y.x += rv.x; y.y += rv.y;
+        }
+        if (p.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); }
+        *reinterpret_cast<float2*>(D + m * p.ldd + col) = y;
+      }
+  }
+}
+
+// =====================================================================================
 // Row gather for the strided shortcut conv (ResBlock.residual: 1x1x1, stride (1,s,s), 'valid',
 // model.py:360-367): copies the sampled pixels (n, t, ho*s, wo*s) into a dense [M_out, C] matrix
 // so that the tensor-core GEMM can consume them through a plain 2-D TMA map.  16-byte vectors,
@@ -494,7 +649,7 @@ int x3d_pw_fwd(const x3d_pw_args* a, void* stream) {
   dim3 grid((unsigned)mt, (a->Nc + kBN - 1) / kBN);
   cudaStream_t st = S(stream);
   if (a->a_dtype == X3D_F32 && a->d_dtype == X3D_F32)
-    pw_gemm_kernel<float, float, false><<<grid, 256, 0, st>>>(p);
+    pw_gemm_tf32x3_kernel<<<grid, 256, 0, st>>>(p);
   else if (a->a_dtype == X3D_BF16 && a->d_dtype == X3D_BF16)
     pw_gemm_kernel<bf16, bf16, true><<<grid, 256, 0, st>>>(p);
   else if (a->a_dtype == X3D_BF16 && a->d_dtype == X3D_F32)

@@ -211,6 +211,145 @@ pw_wgrad_kernel(const float* __restrict__ A, const float* __restrict__ dD, doubl
     }
 }
 
+// The same backward-filter on the tensor cores: dW (TK x TN tile) = A^T (k x rows) . dD (rows x n) as
+// m16n8k8 TF32 MMAs with the 3xTF32 split (hi/lo TF32 halves, lo.hi + hi.lo + hi.hi), fp32
+// accumulators per block, fp64 atomics at the end as above.  8 warps tile the TK x TN block; row
+// chunks of 32 are double-buffered in shared memory, the next chunk is fetched (128-bit loads) while
+// the MMAs of the current one run.  Needs K, N, lda, ldd multiples of 4 (training layouts pad to 8).
+// hi = x rounded to TF32 (half away from zero) with integer ops, lo = x - hi (exact) pre-biased by half a
+// TF32 ulp so that the tensor core's truncation of the low 13 mantissa bits rounds it.  cvt.rna.tf32
+// runs on the 16-lane conversion pipe and made the kernel conversion-bound (measured: 124 MAC/clk/SM).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int TK, int TN>
+__global__ void __launch_bounds__(256)
+pw_wgrad_tf32x3_kernel(const float* __restrict__ A, const float* __restrict__ dD, double* __restrict__ dW, long M,
+                       int K, int N, int lda, int ldd, long rows_per_block, int gather, int Ho, int Wo, int Hi,
+                       int Wi, int stride) {
+  constexpr int RC = 32;
+  constexpr int WN = (TN == 64 && TK == 32) ? 8 : 4, WK = 8 / WN;      // warp grid over the tile
+  constexpr int MF = TK / (16 * WK), NF = TN / (8 * WN);               // m16 / n8 fragments per warp
+  constexpr int PA = TK + 8, PD = TN + 8;                              // pitch = 8 (mod 32): conflict-free fragments
+  constexpr int VA = TK / 32, VD = TN / 32;                            // float4 per thread and chunk
+  __shared__ __align__(16) float sa[2][RC][PA];
+  __shared__ __align__(16) float sd[2][RC][PD];
+  const int k0 = blockIdx.x * TK, n0 = blockIdx.y * TN;
+  const long m0 = (long)blockIdx.z * rows_per_block;
+  long m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wk = (warp / WN) * MF * 16, wn = (warp % WN) * NF * 8;
+
+  float4 ra[VA], rd[VD];
+  auto fetch = [&](long mb) {
+#pragma unroll
+    for (int v = 0; v < VA; ++v) {
+      const int e = tid + v * 256, r = e / (TK / 4), k = (e % (TK / 4)) * 4;
+      const long m = mb + r;
+      ra[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < m1 && k0 + k < K) {
+        long arow = m;
+        if (gather) {
+          long q = m;
+          const int wo = (int)(q % Wo); q /= Wo;
+          const int ho = (int)(q % Ho); q /= Ho;
+          arow = (q * Hi + (long)ho * stride) * Wi + (long)wo * stride;
+        }
+        ra[v] = __ldg(reinterpret_cast<const float4*>(A + arow * lda + k0 + k));
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VD; ++v) {
+      const int e = tid + v * 256, r = e / (TN / 4), nn = (e % (TN / 4)) * 4;
+      const long m = mb + r;
+      rd[v] = (m < m1 && n0 + nn < N) ? __ldg(reinterpret_cast<const float4*>(dD + m * ldd + n0 + nn))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto stage = [&](int buf) {
+#pragma unroll
+    for (int v = 0; v < VA; ++v) {
+      const int e = tid + v * 256;
+      *reinterpret_cast<float4*>(&sa[buf][e / (TK / 4)][(e % (TK / 4)) * 4]) = ra[v];
+    }
+#pragma unroll
+    for (int v = 0; v < VD; ++v) {
+      const int e = tid + v * 256;
+      *reinterpret_cast<float4*>(&sd[buf][e / (TN / 4)][(e % (TN / 4)) * 4]) = rd[v];
+    }
+  };
+
+  // acc: running sums (round-to-nearest fp32 adds); part: the MMA accumulators of one 32-row chunk,
+  // so that the tensor core's truncating accumulation never spans more than 12 MMAs
+  float acc[MF][NF][4], part[MF][NF][4];
+#pragma unroll
+  for (int i = 0; i < MF; ++i)
+#pragma unroll
+    for (int j = 0; j < NF; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[i][j][r] = part[i][j][r] = 0.f;
+
+  fetch(m0);
+  stage(0);
+  __syncthreads();
+  int buf = 0;
+  for (long mb = m0; mb < m1; mb += RC, buf ^= 1) {
+    const bool more = mb + RC < m1;
+    if (more) fetch(mb + RC);
+#pragma unroll
+    for (int ks = 0; ks < RC; ks += 8) {
+      uint32_t ah[MF][4], al[MF][4], bh[NF][2], bl[NF][2];
+#pragma unroll
+      for (int i = 0; i < MF; ++i) {
+        const float* ap = &sa[buf][ks + t][wk + i * 16 + g];
+        split_tf32(ap[0], ah[i][0], al[i][0]);
+        split_tf32(ap[8], ah[i][1], al[i][1]);
+        split_tf32(ap[4 * PA], ah[i][2], al[i][2]);
+        split_tf32(ap[4 * PA + 8], ah[i][3], al[i][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const float* bp = &sd[buf][ks + t][wn + j * 8 + g];
+        split_tf32(bp[0], bh[j][0], bl[j][0]);
+        split_tf32(bp[4 * PD], bh[j][1], bl[j][1]);
+      }
+#pragma unroll
+      for (int term = 0; term < 3; ++term)       // term-major: independent MMAs between dependent ones
+#pragma unroll
+        for (int i = 0; i < MF; ++i)
+#pragma unroll
+          for (int j = 0; j < NF; ++j) mma_tf32(part[i][j], term == 0 ? al[i] : ah[i], term == 1 ? bl[j] : bh[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < MF; ++i)
+#pragma unroll
+      for (int j = 0; j < NF; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { acc[i][j][r] += part[i][j][r]; part[i][j][r] = 0.f; }
+    if (more) stage(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < MF; ++i)
+#pragma unroll
+    for (int j = 0; j < NF; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int k = k0 + wk + i * 16 + g + (r >> 1) * 8, nn = n0 + wn + j * 8 + 2 * t + (r & 1);
+        if (k < K && nn < N) atomicAdd(dW + (long)k * N + nn, (double)acc[i][j][r]);
+      }
+}
+
 // ---------------------------------------------------------------- channelwise 3x3x3 backward
 // backward-data (gather form): dx[n,t,h,w,c] = sum_taps dy[n, t+1-dt, (h+ph-dh)/s, (w+pw-dw)/s, c] * w[tap,c]
 __global__ void __launch_bounds__(256)
@@ -246,13 +385,17 @@ dw_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float
 }
 
 // backward-filter: dw[tap,c] += sum over output pixels x[n, t+dt-1, ho*s+dh-ph, wo*s+dw-pw, c] * dy[n,t,ho,wo,c]
-// A warp (32 consecutive channels, coalesced 128-byte rows) walks whole output rows (n, t, ho)
-// left to right with the 9 x 3 input window of the current output pixel in registers: per output
-// pixel it loads 9 (stride 1) or 18 (stride 2) new values instead of 27 and runs 27 FMAs; row
-// validity (temporal / vertical zero padding) is resolved once per row.
-__global__ void __launch_bounds__(256)
+// A warp (32 consecutive channels, coalesced 128-byte rows) walks whole output rows (n, t, ho) left to
+// right, U output pixels per step: the 9 x ((U-1)*S+3) input values and the U dy values of a step are
+// independent loads issued together (one memory round trip per step; the first version slid a 9x3
+// window one pixel at a time and paid one round trip per pixel: 170 us for a 43 MB stage-5 layer),
+// then 27*U FMAs.  Row validity (temporal / vertical zero padding) is resolved once per row.  The 27
+// per-warp sums meet in shared memory once per block; fp64 atomics.
+template <int S, int U>
+__global__ void __launch_bounds__(256, 2)
 dw_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, double* __restrict__ dwt, int T, int H,
-                int W, int Ho, int Wo, int C, int stride, int ph, int pw, long orows, long rows_per_block) {
+                int W, int Ho, int Wo, int C, int ph, int pw, long orows, long rows_per_block) {
+  constexpr int NC = (U - 1) * S + 3;
   const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const long r0 = (long)blockIdx.y * rows_per_block;
@@ -272,59 +415,60 @@ dw_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, doubl
       for (int dt = 0; dt < 3; ++dt)
 #pragma unroll
         for (int dh = 0; dh < 3; ++dh) {
-          const int ti = t + dt - 1, hi = ho * stride + dh - ph;
+          const int ti = t + dt - 1, hi = ho * S + dh - ph;
           src[dt * 3 + dh] = (ti >= 0 && ti < T && hi >= 0 && hi < H)
                                  ? x + (((n * T + ti) * H + hi) * (long)W) * C + c : nullptr;
         }
       const float* g = dy + row * (long)Wo * C + c;
-      float xv[9][3];
-      // columns wi = wo*stride + dw - pw; prime the window for wo = 0
+      for (int wo0 = 0; wo0 < Wo; wo0 += U) {
+        const int wi0 = wo0 * S - pw;
+        // column offsets (clamped into the row) and validity: warp-uniform, once per step, so that a
+        // load costs one address add and one select (ncu: the first version spent 9 instructions
+        // per FMA on predicated 64-bit addressing)
+        int off[NC];
+        bool ok[NC];
 #pragma unroll
-      for (int k = 0; k < 9; ++k)
-#pragma unroll
-        for (int dw = 0; dw < 3; ++dw) {
-          const int wi = dw - pw;
-          xv[k][dw] = (src[k] != nullptr && wi >= 0 && wi < W) ? __ldg(src[k] + (long)wi * C) : 0.f;
+        for (int j = 0; j < NC; ++j) {
+          const int wi = wi0 + j;
+          ok[j] = wi >= 0 && wi < W;
+          off[j] = min(max(wi, 0), W - 1) * C;
         }
-      for (int wo = 0; wo < Wo; ++wo) {
-        const float gv = __ldg(g + (long)wo * C);
+        float xv[9][NC], gv[U];
 #pragma unroll
-        for (int k = 0; k < 9; ++k)
+        for (int u = 0; u < U; ++u) gv[u] = (wo0 + u < Wo) ? __ldg(g + (wo0 + u) * C) : 0.f;
 #pragma unroll
-          for (int dw = 0; dw < 3; ++dw) acc[k * 3 + dw] = fmaf(xv[k][dw], gv, acc[k * 3 + dw]);
-        if (wo + 1 < Wo) {                   // slide to the next output pixel
-          const int wn = (wo + 1) * stride - pw;          // its leftmost column
-          if (stride == 1) {
-            const int wi = wn + 2;
-            const bool ok = wi < W;
+        for (int k = 0; k < 9; ++k) {
+          if (src[k] != nullptr) {            // uniform: depends on (t, ho) only
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-              xv[k][0] = xv[k][1]; xv[k][1] = xv[k][2];
-              xv[k][2] = (ok && src[k] != nullptr) ? __ldg(src[k] + (long)wi * C) : 0.f;
+            for (int j = 0; j < NC; ++j) {
+              const float v = __ldg(src[k] + off[j]);
+              xv[k][j] = ok[j] ? v : 0.f;
             }
           } else {
-            const bool ok1 = wn + 1 < W, ok2 = wn + 2 < W;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-              xv[k][0] = xv[k][2];
-              xv[k][1] = (ok1 && src[k] != nullptr) ? __ldg(src[k] + (long)(wn + 1) * C) : 0.f;
-              xv[k][2] = (ok2 && src[k] != nullptr) ? __ldg(src[k] + (long)(wn + 2) * C) : 0.f;
-            }
+            for (int j = 0; j < NC; ++j) xv[k][j] = 0.f;
           }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int k = 0; k < 9; ++k)
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw) acc[k * 3 + dw] = fmaf(xv[k][u * S + dw], gv[u], acc[k * 3 + dw]);
       }
     }
   }
-  __shared__ float sh[8][32];
-  for (int tap = 0; tap < 27; ++tap) {
-    sh[ry][lane] = acc[tap];
-    __syncthreads();
-    if (ry == 0 && c < C) {
-      double s = 0.0;
-      for (int i = 0; i < 8; ++i) s += sh[i][lane];
-      atomicAdd(dwt + (long)tap * C + c, s);
-    }
-    __syncthreads();
+  __shared__ float sh[8][27][32];
+#pragma unroll
+  for (int tap = 0; tap < 27; ++tap) sh[ry][tap][lane] = acc[tap];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 27 * 32; e += 256) {
+    const int tap = e >> 5, l = e & 31;
+    if (blockIdx.x * 32 + l >= C) continue;
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += sh[i][tap][l];
+    atomicAdd(dwt + (long)tap * C + blockIdx.x * 32 + l, sum);
   }
 }
 
@@ -734,10 +878,21 @@ int x3d_pw_wgrad(const float* A, const float* dD, double* dW, int64_t M, int K, 
   if (zb > 65535) { rpb = ((M + 65534) / 65535 + 31) / 32 * 32; zb = (M + rpb - 1) / rpb; }
   dim3 grid((K + TK - 1) / TK, (N + TN - 1) / TN, (unsigned)zb);
 #define X3D_WG(TKK, TNN) train::pw_wgrad_kernel<TKK, TNN><<<grid, 256, 0, S(stream)>>>(A, dD, dW, M, K, N, lda, ldd, rpb, gather, Ho, Wo, Hi, Wi, stride)
-  if (k64 && n64) X3D_WG(64, 64);
-  else if (k64) X3D_WG(64, 32);
-  else if (n64) X3D_WG(32, 64);
-  else X3D_WG(32, 32);
+#define X3D_WGT(TKK, TNN) train::pw_wgrad_tf32x3_kernel<TKK, TNN><<<grid, 256, 0, S(stream)>>>(A, dD, dW, M, K, N, lda, ldd, rpb, gather, Ho, Wo, Hi, Wi, stride)
+  const bool vec = K % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && ldd % 4 == 0 &&
+                   reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(dD) % 16 == 0;
+  if (vec) {
+    if (k64 && n64) X3D_WGT(64, 64);
+    else if (k64) X3D_WGT(64, 32);
+    else if (n64) X3D_WGT(32, 64);
+    else X3D_WGT(32, 32);
+  } else {
+    if (k64 && n64) X3D_WG(64, 64);
+    else if (k64) X3D_WG(64, 32);
+    else if (n64) X3D_WG(32, 64);
+    else X3D_WG(32, 32);
+  }
+#undef X3D_WGT
 #undef X3D_WG
   return check_launch("x3d_pw_wgrad");
 }
@@ -756,11 +911,18 @@ int x3d_dw_wgrad(const float* x, const float* dy, double* dwt, int N, int T, int
   X3D_REQUIRE(x && dy && dwt && N > 0 && T > 0 && H > 0 && W > 0 && C > 0 && (stride == 1 || stride == 2), X3D_ERR_INVALID_ARG, "x3d_dw_wgrad: bad argument");
   const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
   const long orows = (long)N * T * Ho;                    // output rows; a warp walks whole rows
-  long rpb = 16;
+  const int cb = (C + 31) / 32;
+  // ~8 blocks per SM in total, at least 16 rows (two per warp) each: fewer blocks = fewer atomics
+  long rpb = (orows * cb + 148L * 8 - 1) / (148L * 8);
+  if (rpb < 16) rpb = 16;
+  rpb = (rpb + 7) / 8 * 8;
   long yb = (orows + rpb - 1) / rpb;
-  if (yb > 65535) { rpb = (orows + 65534) / 65535; yb = (orows + rpb - 1) / rpb; }
-  dim3 grid((C + 31) / 32, (unsigned)yb);
-  dw_wgrad_kernel<<<grid, 256, 0, S(stream)>>>(x, dy, dwt, T, H, W, Ho, Wo, C, stride, pad_h, pad_w, orows, rpb);
+  if (yb > 65535) { rpb = ((orows + 65534) / 65535 + 7) / 8 * 8; yb = (orows + rpb - 1) / rpb; }
+  dim3 grid(cb, (unsigned)yb);
+  if (stride == 1)
+    train::dw_wgrad_kernel<1, 4><<<grid, 256, 0, S(stream)>>>(x, dy, dwt, T, H, W, Ho, Wo, C, pad_h, pad_w, orows, rpb);
+  else
+    train::dw_wgrad_kernel<2, 2><<<grid, 256, 0, S(stream)>>>(x, dy, dwt, T, H, W, Ho, Wo, C, pad_h, pad_w, orows, rpb);
   return check_launch("x3d_dw_wgrad");
 }
 
