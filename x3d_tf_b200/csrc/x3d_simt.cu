@@ -131,8 +131,10 @@ se_mlp_kernel(const float* __restrict__ partial, int nblk, float inv_count,
   for (int cb = 0; cb < C; cb += CP) {
     const int c = cb + (tid % CP), kg = tid / CP;
     float a = 0.f;
-    if (c < C)
-      for (int k = kg; k < nblk; k += KG) a += p[(long)k * C + c];
+    if (c < C) {
+#pragma unroll 4
+      for (int k = kg; k < nblk; k += KG) a += __ldg(p + (long)k * C + c);
+    }
     red[tid] = a;
     __syncthreads();
     if (kg == 0 && c < C) {
@@ -141,18 +143,38 @@ se_mlp_kernel(const float* __restrict__ partial, int nblk, float inv_count,
     }
     __syncthreads();
   }
-  const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
-  for (int j = warp; j < Cw; j += nwarp) {
+  // fc1: thread tid walks w1 (row-major [C][Cw]) at tid, tid + 256, ...: coalesced, independent loads
+  // (a warp per output column with a strided walk over C was a chain of ~14 exposed L2 round trips per
+  // column: 20 of the kernel's 21 us).  Column j = tid % Cw is fixed per thread when Cw divides 256;
+  // the 256 / Cw partial sums of a column meet in shared memory.
+  if (256 % Cw == 0) {
+    const int j = tid % Cw, G = 256 / Cw;
+    const int total = C * Cw;
     float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(mean[c], w1[(long)c * Cw + j], a);
+#pragma unroll 8
+    for (int e = tid; e < total; e += 256) a = fmaf(mean[e / Cw], __ldg(w1 + e), a);
+    red[tid] = a;
+    __syncthreads();
+    if (tid < Cw) {
+      float zsum = 0.f;
+      for (int g = 0; g < G; ++g) zsum += red[g * Cw + j];
+      z[j] = fmaxf(zsum + b1[j], 0.f);
+    }
+  } else {
+    const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    for (int j = warp; j < Cw; j += nwarp) {
+      float a = 0.f;
+      for (int c = lane; c < C; c += 32) a = fmaf(mean[c], w1[(long)c * Cw + j], a);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) z[j] = fmaxf(a + b1[j], 0.f);
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) z[j] = fmaxf(a + b1[j], 0.f);
+    }
   }
   __syncthreads();
   for (int c = tid; c < C; c += blockDim.x) {
     float a = b2[c];
-    for (int j = 0; j < Cw; ++j) a = fmaf(z[j], w2[(long)j * C + c], a);
+#pragma unroll 8
+    for (int j = 0; j < Cw; ++j) a = fmaf(z[j], __ldg(w2 + (long)j * C + c), a);
     scale[(long)n * C + c] = 1.f / (1.f + expf(-a));
   }
 }
