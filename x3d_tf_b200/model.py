@@ -211,11 +211,49 @@ class PointwiseConv:
         wp = _pad_to(_pad_to(k2.T, 0, npad), 1, kpad)
         self.wp = torch.from_numpy(np.ascontiguousarray(wp, dtype=np.float32)).to(device).to(
             torch.bfloat16).contiguous()
+        self._k2t = _pad_to(_pad_to(k2.T, 0, self.Ns), 1, self.Ks)               # [Ns, Ks], fp64
+        self._paired: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    # Pixel pairing (Options.pair_pixels): rows of 24 or 56 bf16 channels are 48 / 112 bytes and straddle
+    # 32-byte sectors, so TMA moves 1.33x / 1.14x the useful bytes between L2 and shared memory, and a
+    # 128-row tile of them is small against the per-tile cost of the GEMM pipeline.  P consecutive
+    # pixels form one row (the activation is contiguous, so this is only a different view) and the
+    # weight becomes blockdiag(W, ..., W): [M/P, P*K] x [P*K, P*N].  The extra MMA work is on exact
+    # zeros and the tensor pipe is far from busy; results are bit-identical to the unpaired GEMM.
+    def _pair_factor(self, M: int, rows_per_clip: int) -> int:
+        for P in (4, 2):
+            if P > Options.pair_pixels or M % P or (rows_per_clip and rows_per_clip % P):
+                continue
+            if P * self.Ks > Options.pair_max_k or P * self.Ns > 256:
+                continue
+            if not Options.pair_aligned and self.Ks % 16 == 0 and self.Ns % 16 == 0:
+                continue
+            return P
+        return 1
+
+    def _paired_weights(self, P: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+        if P not in self._paired:
+            w = np.zeros((P * self.Ns, P * self.Ks), np.float64)
+            for i in range(P):
+                w[i * self.Ns:(i + 1) * self.Ns, i * self.Ks:(i + 1) * self.Ks] = self._k2t
+            npad, kpad = (P * self.Ns + 15) // 16 * 16, (P * self.Ks + 63) // 64 * 64
+            w = _pad_to(_pad_to(w, 0, npad), 1, kpad)
+            wp = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)).to(device).to(
+                torch.bfloat16).contiguous()
+            self._paired[P] = (wp, self.bias.repeat(P).contiguous())
+        return self._paired[P]
 
     def run(self, a: torch.Tensor, M: int, *, use_tc: bool, out_dtype=None, residual=None,
             se=None, rows_per_clip=0, swish=False, relu=False, gather=None) -> torch.Tensor:
         if use_tc and a.dtype == torch.bfloat16 and gather is None and \
                 (out_dtype is None or out_dtype == torch.bfloat16):
+            P = self._pair_factor(M, rows_per_clip if se is not None else 0)
+            if P > 1 and a.is_contiguous() and (residual is None or residual.is_contiguous()):
+                wp, bias = self._paired_weights(P, a.device)
+                se_p = None if se is None else se.repeat(1, P)       # per-clip channel scales, once per pixel slot
+                return ops.pw_tc_fwd(a, wp, bias, M=M // P, K=P * self.Ks, Nc=P * self.Ns, residual=residual,
+                                     se=se_p, rows_per_clip=rows_per_clip // P, swish=swish,
+                                     relu=relu).view(M, self.Ns)
             return ops.pw_tc_fwd(a, self.wp, self.bias, M=M, K=self.Ks, Nc=self.Ns,
                                  residual=residual, se=se, rows_per_clip=rows_per_clip,
                                  swish=swish, relu=relu)
@@ -242,6 +280,11 @@ class Options:
     # is the FMA/issue-bound kernel), step 11.91 -> 11.75 ms (+1.4 % clips/s); X3D_SWISH_IN_DW=0 turns
     # it off.
     swish_in_dw = os.environ.get("X3D_SWISH_IN_DW", "1") == "1"
+    # pointwise convs whose rows are not a multiple of 32 bytes (24 / 56 channels): two pixels per GEMM
+    # row with a block-diagonal weight (PointwiseConv); X3D_PAIR_PIXELS=0 turns it off.
+    pair_pixels = int(os.environ.get("X3D_PAIR_PIXELS", "2"))       # largest pairing factor (1 = off, 2, 4)
+    pair_max_k = int(os.environ.get("X3D_PAIR_MAX_K", "256"))
+    pair_aligned = os.environ.get("X3D_PAIR_ALIGNED", "0") == "1"   # also pair rows that are sector-aligned
 
 
 def _use_tc() -> bool:
