@@ -216,3 +216,50 @@ def test_full_size_properties(variant, T, S, views, clips):
     mg, *_ = _model(variant, dtype="bfloat16", views=views, graph=True)
     mg(xd); mg(xd)
     assert torch.equal(mg.last_logits, logits)
+
+
+@pytest.mark.parametrize("K,N,residual,swish", [(24, 54, False, False), (54, 24, True, False),
+                                                (24, 24, False, False), (54, 24, True, True)])
+def test_pixel_pairing_bf16_is_bit_identical(K, N, residual, swish):
+    """PointwiseConv's pixel pairing ([M/2, 2K] x blockdiag(W, W)) only adds exact zeros to each
+    accumulator, but groups a pixel's products into K=16 MMA steps differently: with and without it
+    (factors 2 and 4) the tcgen05 path must agree to fp32-accumulation rounding, i.e. at most one bf16
+    ulp on a handful of outputs, including an odd tile count and the residual / swish variants."""
+    from x3d_tf_b200 import model as M
+    rng = np.random.default_rng(7)
+    Mrows = 4 * 1237                                   # divisible by 4, not by the 128-row tile
+    ks, ns = (K + 7) // 8 * 8, (N + 7) // 8 * 8
+    kern = rng.normal(size=(1, 1, 1, K, N)).astype(np.float32) * 0.2
+    scale, shift = rng.uniform(0.5, 1.5, N), rng.normal(size=N) * 0.1
+    a = torch.zeros(Mrows, ks, dtype=torch.bfloat16, device=dev())
+    a[:, :K] = torch.from_numpy(rng.normal(size=(Mrows, K)).astype(np.float32)).to(dev()).to(torch.bfloat16)
+    r = None
+    if residual:
+        r = torch.zeros(Mrows, ns, dtype=torch.bfloat16, device=dev())
+        r[:, :N] = torch.from_numpy(rng.normal(size=(Mrows, N)).astype(np.float32)).to(dev()).to(torch.bfloat16)
+    pc = M.PointwiseConv(kern, scale, shift, dev())
+    saved = (M.Options.pair_pixels, M.Options.pair_aligned)
+    outs = {}
+    try:
+        for P in (1, 2, 4):
+            M.Options.pair_pixels, M.Options.pair_aligned = P, False
+            assert pc._pair_factor(Mrows) == P
+            outs[P] = pc.run(a, Mrows, use_tc=True, residual=r, swish=swish, relu=True).clone()
+        torch.cuda.synchronize()
+    finally:
+        M.Options.pair_pixels, M.Options.pair_aligned = saved
+    assert outs[1].shape == (Mrows, ns)
+    for P in (2, 4):
+        d = (outs[P].float() - outs[1].float()).abs()
+        assert float((d > 0).float().mean()) < 1e-3, (P, float((d > 0).float().mean()))
+        assert bool((d <= outs[1].float().abs() * 2.0 ** -7 + 1e-30).all()), P
+    want = a[:, :K].double() @ torch.from_numpy(kern.reshape(K, N) * scale[None, :]).to(dev()) + \
+        torch.from_numpy(shift).to(dev())
+    if swish:
+        x = a[:, :K].double()
+        want = (x * torch.sigmoid(x)) @ torch.from_numpy(kern.reshape(K, N) * scale[None, :]).to(dev()) + \
+            torch.from_numpy(shift).to(dev())
+    if residual:
+        want = want + r[:, :N].double()
+    want = torch.relu(want)
+    assert rel_err(to_np(outs[2][:, :N].float()), to_np(want)) < BF16_TOL

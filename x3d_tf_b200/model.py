@@ -219,8 +219,11 @@ class PointwiseConv:
     # 128-row tile of them is small against the per-tile cost of the GEMM pipeline.  P consecutive
     # pixels form one row (the activation is contiguous, so this is only a different view) and the
     # weight becomes blockdiag(W, ..., W): [M/P, P*K] x [P*K, P*N].  The extra MMA work is on exact
-    # zeros and the tensor pipe is far from busy; results are bit-identical to the unpaired GEMM.
-    def _pair_factor(self, M: int, rows_per_clip: int) -> int:
+    # zeros and the tensor pipe is far from busy.  The products of a pixel are grouped into K=16 MMA
+    # steps differently than in the unpaired GEMM, so results agree to fp32-accumulation rounding
+    # (at most one bf16 ulp after the output rounding), not bit for bit; pairs never straddle clips
+    # (rows_per_clip % P == 0), which keeps a clip's result independent of its position in the batch.
+    def _pair_factor(self, M: int, rows_per_clip: int = 0) -> int:
         for P in (4, 2):
             if P > Options.pair_pixels or M % P or (rows_per_clip and rows_per_clip % P):
                 continue
@@ -244,16 +247,16 @@ class PointwiseConv:
         return self._paired[P]
 
     def run(self, a: torch.Tensor, M: int, *, use_tc: bool, out_dtype=None, residual=None,
-            se=None, rows_per_clip=0, swish=False, relu=False, gather=None) -> torch.Tensor:
+            se=None, rows_per_clip=0, swish=False, relu=False, gather=None, pair_rows=0) -> torch.Tensor:
         if use_tc and a.dtype == torch.bfloat16 and gather is None and \
                 (out_dtype is None or out_dtype == torch.bfloat16):
-            P = self._pair_factor(M, rows_per_clip if se is not None else 0)
+            # (not with an SE scale: that prologue indexes the scale by column, and pairing measured no
+            # gain on the projection GEMMs anyway)
+            P = self._pair_factor(M, pair_rows or rows_per_clip) if se is None else 1
             if P > 1 and a.is_contiguous() and (residual is None or residual.is_contiguous()):
                 wp, bias = self._paired_weights(P, a.device)
-                se_p = None if se is None else se.repeat(1, P)       # per-clip channel scales, once per pixel slot
                 return ops.pw_tc_fwd(a, wp, bias, M=M // P, K=P * self.Ks, Nc=P * self.Ns, residual=residual,
-                                     se=se_p, rows_per_clip=rows_per_clip // P, swish=swish,
-                                     relu=relu).view(M, self.Ns)
+                                     swish=swish, relu=relu).view(M, self.Ns)
             return ops.pw_tc_fwd(a, self.wp, self.bias, M=M, K=self.Ks, Nc=self.Ns,
                                  residual=residual, se=se, rows_per_clip=rows_per_clip,
                                  swish=swish, relu=relu)
@@ -281,7 +284,9 @@ class Options:
     # it off.
     swish_in_dw = os.environ.get("X3D_SWISH_IN_DW", "1") == "1"
     # pointwise convs whose rows are not a multiple of 32 bytes (24 / 56 channels): two pixels per GEMM
-    # row with a block-diagonal weight (PointwiseConv); X3D_PAIR_PIXELS=0 turns it off.
+    # row with a block-diagonal weight (PointwiseConv).  Measured at 80 clips of 16x256^2 (step, a,
+    # shortcut in ms): off 11.66 / 2.95 / 0.52; factor 2 10.97 / 2.47 / 0.37; factor 4 11.07; factor 2
+    # also on sector-aligned rows (X3D_PAIR_ALIGNED=1) 11.23.  X3D_PAIR_PIXELS=1 turns it off.
     pair_pixels = int(os.environ.get("X3D_PAIR_PIXELS", "2"))       # largest pairing factor (1 = off, 2, 4)
     pair_max_k = int(os.environ.get("X3D_PAIR_MAX_K", "256"))
     pair_aligned = os.environ.get("X3D_PAIR_ALIGNED", "0") == "1"   # also pair rows that are sector-aligned
@@ -451,7 +456,7 @@ class Bottleneck(Layer):
             swish_in_b = False
         else:
             ops.Profiler.tag = "a"
-            a = d["a"].run(x, N * T * H * W, use_tc=tc, relu=True).view(N, T, H, W, ci)
+            a = d["a"].run(x, N * T * H * W, use_tc=tc, relu=True, pair_rows=T * H * W).view(N, T, H, W, ci)
             ops.Profiler.tag = "b"
             # blocks without SE: the swish that follows bn_b goes into the stencil's epilogue, so the
             # projection GEMM runs without its transform warps (its fastest form)
@@ -519,7 +524,7 @@ class ResBlock(Layer):
             if _use_tc() and x.dtype == torch.bfloat16:
                 # sampled pixels -> dense matrix -> tensor-core GEMM (bn_r folded)
                 rows = x.view(-1, x.shape[-1]) if s == 1 else ops.gather_rows_fwd(x, s)
-                res = d["r"].run(rows, N * T * Ho * Wo, use_tc=True)
+                res = d["r"].run(rows, N * T * Ho * Wo, use_tc=True, pair_rows=T * Ho * Wo)
             else:
                 res = d["r"].run(x, N * T * Ho * Wo, use_tc=False, gather=(T, Ho, Wo, H, W, s))
         else:
