@@ -80,7 +80,10 @@ int x3d_stem_tc_fwd(const void* in, int in_dtype, const void* wc, const float* b
  *   pro(a) = a                         if se == NULL and !swish
  *          = swish(a * se[m / rows_per_clip, k])   (se NULL => factor 1; swish(x)=x*sigmoid(x))
  *   R    [M, ldr]   residual, d_dtype (may be NULL);  act = ReLU if relu else identity
- *   D    [M, ldd]   d_dtype */
+ *   D    [M, ldd]   d_dtype
+ * Accumulation is fp32.  fp32 in / fp32 out runs on the tensor cores with the 3xTF32 split (each
+ * operand = two TF32 halves; lo.hi + hi.lo + hi.hi): fp32-level accuracy, 2e-7..4e-6 of the
+ * output scale measured; bf16 activations run on CUDA cores (the tcgen05 path is x3d_pw_tc_fwd). */
 typedef struct x3d_pw_args {
   const void* A; const float* Wt; const float* bias; const void* R; const float* se; void* D;
   int64_t M; int32_t K, Nc, lda, ldw, ldr, ldd;
@@ -216,7 +219,9 @@ int x3d_bn_bwd_apply(const float* dy, const float* x, const float* relu_out, con
 int x3d_d2f(const double* in, float* out, int64_t n, float scale, void* stream);
 /* Backward-filter of a 1x1x1 conv (a, c, residual, conv5, fc1, fc2, se_fc1, se_fc2):
  * dW[k,n] += sum_m A[row(m),k] * dD[m,n]; gather/geometry as in x3d_pw_fwd.  (Backward-data is
- * x3d_pw_fwd with the transposed kernel.) */
+ * x3d_pw_fwd with the transposed kernel.)  3xTF32 tensor-core path when K, N, lda, ldd are multiples
+ * of 4 and the pointers 16-byte aligned (fp32 partial sums per 32-row chunk), CUDA cores otherwise;
+ * fp64 atomics into dW either way. */
 int x3d_pw_wgrad(const float* A, const float* dD, double* dW, int64_t M, int K, int N, int lda,
                  int ldd, int gather, int Ho, int Wo, int Hi, int Wi, int stride, void* stream);
 /* Backward-data / backward-filter of the channelwise 3x3x3 conv (Bottleneck.b, model.py:259-267) */
