@@ -90,7 +90,13 @@ struct InputNorm {
   float mean[3], std[3], norm_value;
 };
 
-template <typename TI>
+// kStaged (bf16 input, even W): the 17 x 33-pixel input patch of a frame is copied into a 3-deep
+// shared-memory ring with 4-byte cp.async (7 per thread and frame, zero fill = the conv's padding) two
+// frames ahead, and every worker assembles its 27 taps from 15 shared-memory words; otherwise every
+// worker gathers its 27 taps with 2-byte global loads.
+constexpr int kSW = 50, kSRows = 2 * kTH + 1, kSWords = kSW * kSRows, kSRing = 3, kSBytes = 3456;
+
+template <typename TI, bool kStaged>
 // (capping the registers for a third CTA per SM serialises the loads again: 0.675 ms vs 0.605 ms)
 __global__ void __launch_bounds__(kThreads)
 stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const float* __restrict__ bias,
@@ -108,6 +114,7 @@ stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const fl
   uint64_t* t_empty = t_full + 2;                                 // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
   unsigned short* s_lut = reinterpret_cast<unsigned short*>(tmem_slot + 4);
+  const uint32_t stage_s = smem_u32(s_lut + 768);          // [kSRing][kSBytes] input patches (kStaged)
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int n = blockIdx.z;
@@ -171,6 +178,108 @@ stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const fl
     const int q = warp;                                    // TMEM lane quarter of this warp
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
+    auto epilogue = [&](int t) {
+      // ---- epilogue of output frame t
+      const int as = t & 1;
+      mbar_wait(&t_full[as], static_cast<uint32_t>((t >> 1) & 1));
+      tcgen05_after_sync();
+      bf16* dst = dst0 + t * out_frame;
+#pragma unroll
+      for (int c8 = 0; c8 < kN; c8 += 8) {
+        if (c8 < C) {                                   // uniform
+          uint32_t v[8];
+          tmem_ld8(t_lane + as * kN + c8, v);
+          tmem_ld_wait();
+          if (pix_ok) {
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              y[j] = fmaxf(__uint_as_float(v[j]) + s_bias[c8 + j], 0.f);
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(y[4], y[5]);
+            __nv_bfloat162 p3 = __floats2bfloat162_rn(y[6], y[7]);
+            uint4 o;
+            o.x = *reinterpret_cast<uint32_t*>(&p0);
+            o.y = *reinterpret_cast<uint32_t*>(&p1);
+            o.z = *reinterpret_cast<uint32_t*>(&p2);
+            o.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(dst + c8) = o;
+          }
+        }
+      }
+      tcgen05_before_sync();
+      mbar_arrive(&t_empty[as]);
+    };
+
+    if constexpr (kStaged) {
+      // ---- staged loader: word idx = tid + 128 j of the [17][50]-word patch; its source offset inside
+      // a frame (bytes) is fixed for the whole march, -1 = outside the image (zero = conv padding)
+      const long row_bytes = static_cast<long>(W) * 6;
+      const char* in_n = reinterpret_cast<const char*>(in) + static_cast<long>(n) * T * frame_elems * 2;
+      long soff[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int idx = tid + j * 128;
+        const int rr = idx / kSW, ww = idx - rr * kSW;
+        const int h = 2 * ho0 - 1 + rr;
+        const long off = 12L * wo0 - 8 + 4L * ww;          // word 0 starts 2 bytes before pixel 2*wo0-1
+        soff[j] = (idx < kSWords && h >= 0 && h < H && off >= 0 && off < row_bytes) ? h * row_bytes + off : -1;
+      }
+      auto issue_frame = [&](int f) {
+        if (f < T) {
+          const char* fr = in_n + static_cast<long>(f) * frame_elems * 2;
+          const uint32_t dstb = stage_s + (f % kSRing) * kSBytes + tid * 4;
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            if (tid + j * 128 < kSWords) {
+              const bool ok = soff[j] >= 0;
+              const char* src = ok ? fr + soff[j] : reinterpret_cast<const char*>(in);
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dstb + j * 512), "l"(src),
+                           "r"(ok ? 4 : 0)
+                           : "memory");
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");   // one group per frame, empty past the end
+      };
+      issue_frame(0);
+      issue_frame(1);
+      for (int i = 0; i < T + 3; ++i) {
+        if (i < T) {
+          asm volatile("cp.async.wait_group 1;" ::: "memory");   // frame i has landed (i+1 may be in flight)
+          asm volatile("bar.sync 1, 128;" ::: "memory");         // ... for every worker; frame i-1 fully read
+          const uint32_t sb = stage_s + (i % kSRing) * kSBytes + ((2 * py) * kSW + 3 * px) * 4;
+          uint32_t w[3][5];
+#pragma unroll
+          for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[dh][j]) : "r"(sb + (dh * kSW + j) * 4));
+          // halfword m of a row = tap (dw, ci) = m - 1; the im2col row is the 27 taps in (dh, dw, ci) order
+          uint32_t pk[14];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            pk[j] = __byte_perm(w[0][j], w[0][j + 1], 0x5432);
+            pk[5 + j] = w[1][j + 1];
+            pk[9 + j] = __byte_perm(w[2][j], w[2][j + 1], 0x5432);
+          }
+          pk[4] = __byte_perm(w[0][4], w[1][0], 0x7632);
+          pk[13] = w[2][4] >> 16;
+          const uint32_t blk = a_s + (i % kRing) * kABytes + a_row;
+#pragma unroll
+          for (int k = 0; k < 28; k += 2)
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(blk + (k >> 3) * (kPix * 16) + (k & 7) * 2),
+                         "r"(pk[k >> 1])
+                         : "memory");
+          fence_proxy_async();
+          mbar_arrive(&built[i % kRing]);
+          issue_frame(i + 2);
+        }
+        if (i >= 3) epilogue(i - 3);
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
     // The kernel is bound by the latency of these 27 scattered loads per pixel and frame, so two
     // frames are kept in flight: the loads of frame i+2 are issued when frame i is published, one
     // whole iteration (publish + epilogue) before they are needed.
@@ -207,40 +316,8 @@ stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const fl
         if (i & 1) publish(i, vb);
         else publish(i, va);
       }
-      const int t = i - 3;
-      if (t >= 0) {
-        // ---- epilogue of output frame t
-        const int as = t & 1;
-        mbar_wait(&t_full[as], static_cast<uint32_t>((t >> 1) & 1));
-        tcgen05_after_sync();
-        bf16* dst = dst0 + t * out_frame;
-#pragma unroll
-        for (int c8 = 0; c8 < kN; c8 += 8) {
-          if (c8 < C) {                                   // uniform
-            uint32_t v[8];
-            tmem_ld8(t_lane + as * kN + c8, v);
-            tmem_ld_wait();
-            if (pix_ok) {
-              float y[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                y[j] = fmaxf(__uint_as_float(v[j]) + s_bias[c8 + j], 0.f);
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
-              __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(y[4], y[5]);
-              __nv_bfloat162 p3 = __floats2bfloat162_rn(y[6], y[7]);
-              uint4 o;
-              o.x = *reinterpret_cast<uint32_t*>(&p0);
-              o.y = *reinterpret_cast<uint32_t*>(&p1);
-              o.z = *reinterpret_cast<uint32_t*>(&p2);
-              o.w = *reinterpret_cast<uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(dst + c8) = o;
-            }
-          }
-        }
-        tcgen05_before_sync();
-        mbar_arrive(&t_empty[as]);
-      }
+      if (i >= 3) epilogue(i - 3);
+    }
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer (warp 4)
@@ -280,32 +357,40 @@ stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const fl
   }
 }
 
-constexpr size_t kSmemBytes = 128 + kRing * kABytes + kKT * kWBytes + 128 + 128 + 16 + 768 * 2;
+constexpr size_t kSmemBytes = 128 + kRing * kABytes + kKT * kWBytes + 128 + 128 + 16 + 768 * 2 + kSRing * kSBytes;
 
 }  // namespace stemtc
 }  // namespace x3d
 
 using namespace x3d;
 
-template <typename TI>
-static int stem_tc_launch(const void* in, const void* wc, const float* bias, void* out, int N, int T, int H,
-                          int W, int C, const stemtc::InputNorm& nrm, cudaStream_t st) {
+template <typename TI, bool kStaged>
+static int stem_tc_launch_impl(const void* in, const void* wc, const float* bias, void* out, int N, int T, int H,
+                               int W, int C, const stemtc::InputNorm& nrm, cudaStream_t st) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   dim3 grid((Wo + stemtc::kTW - 1) / stemtc::kTW, (Ho + stemtc::kTH - 1) / stemtc::kTH, N);
   X3D_REQUIRE(grid.y <= 65535, X3D_ERR_UNSUPPORTED, "x3d_stem_tc_fwd: image too tall");
-  static bool configured = false;                   // one flag per input type (template instance)
+  static bool configured = false;                   // one flag per template instance
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(stemtc::stem_tc_kernel<TI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(stemtc::stem_tc_kernel<TI, kStaged>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)stemtc::kSmemBytes);
     X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_stem_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
-    cudaFuncSetAttribute(stemtc::stem_tc_kernel<TI>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(stemtc::stem_tc_kernel<TI, kStaged>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  stemtc::stem_tc_kernel<TI><<<grid, stemtc::kThreads, stemtc::kSmemBytes, st>>>(
+  stemtc::stem_tc_kernel<TI, kStaged><<<grid, stemtc::kThreads, stemtc::kSmemBytes, st>>>(
       static_cast<const TI*>(in), static_cast<const uint4*>(wc), bias, static_cast<bf16*>(out), T, H, W, Ho, Wo,
       C, nrm);
   return check_launch("x3d_stem_tc_fwd");
+}
+
+template <typename TI>
+static int stem_tc_launch(const void* in, const void* wc, const float* bias, void* out, int N, int T, int H,
+                          int W, int C, const stemtc::InputNorm& nrm, cudaStream_t st) {
+  if (sizeof(TI) == 2 && W % 2 == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0)
+    return stem_tc_launch_impl<TI, sizeof(TI) == 2>(in, wc, bias, out, N, T, H, W, C, nrm, st);
+  return stem_tc_launch_impl<TI, false>(in, wc, bias, out, N, T, H, W, C, nrm, st);
 }
 
 static int stem_tc_check(const void* in, const void* wc, const float* bias, void* out, int N, int T, int H,
