@@ -380,13 +380,17 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// TN = 64: 4 x 2 warps of 32 x 32; TN = 32 (Nc <= 32, e.g. the 24-channel projections): 8 x 1 warps of
+// 16 x 32, so that no warp sits on columns beyond Nc.
+template <int TN>
 __global__ void __launch_bounds__(256, 2)
 pw_gemm_tf32x3_kernel(const PwParams p) {
+  constexpr int MF = TN == 64 ? 2 : 1, WPitch = TN + 8;
   __shared__ __align__(16) float As[2][kBM][kTAPitch];
-  __shared__ __align__(16) float Ws[2][kBK][kTWPitch];
+  __shared__ __align__(16) float Ws[2][kBK][WPitch];
   const int tid = threadIdx.x;
   const long m0 = (long)blockIdx.x * kBM;
-  const int n0 = blockIdx.y * kBN;
+  const int n0 = blockIdx.y * TN;
   const float* A = static_cast<const float*>(p.A);
 
   // loader roles as in pw_gemm_kernel: A row lr / k-half lk, W row wk / 4 columns from wn
@@ -426,20 +430,20 @@ pw_gemm_tf32x3_kernel(const PwParams p) {
       for (int i = 0; i < 8; ++i) av[i] = 0.f;
     }
     wv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k0 + wk < p.K && n0 + wn < p.Nc)
+    if (k0 + wk < p.K && wn < TN && n0 + wn < p.Nc)
       wv = __ldg(reinterpret_cast<const float4*>(p.Wt + (long)(k0 + wk) * p.ldw + n0 + wn));
   };
   auto stage = [&](int buf) {
     *reinterpret_cast<float4*>(&As[buf][lr][lk]) = make_float4(av[0], av[1], av[2], av[3]);
     *reinterpret_cast<float4*>(&As[buf][lr][lk + 4]) = make_float4(av[4], av[5], av[6], av[7]);
-    *reinterpret_cast<float4*>(&Ws[buf][wk][wn]) = wv;
+    if (wn < TN) *reinterpret_cast<float4*>(&Ws[buf][wk][wn]) = wv;
   };
 
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int wm = (warp & 3) * 32, wc = (warp >> 2) * 32;
-  float acc[2][4][4];
+  const int wm = TN == 64 ? (warp & 3) * 32 : warp * 16, wc = TN == 64 ? (warp >> 2) * 32 : 0;
+  float acc[MF][4][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < MF; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -455,9 +459,9 @@ pw_gemm_tf32x3_kernel(const PwParams p) {
 #pragma unroll
     for (int ks = 0; ks < kBK; ks += 8) {
       if (kt * kBK + ks >= p.K) break;               // K is a multiple of 8: skip an all-zero half
-      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+      uint32_t ah[MF][4], al[MF][4], bh[4][2], bl[4][2];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < MF; ++i) {
         const float* ap = &As[buf][wm + i * 16 + g][ks + t];
         split_tf32(ap[0], ah[i][0], al[i][0]);
         split_tf32(ap[8 * kTAPitch], ah[i][1], al[i][1]);
@@ -468,7 +472,7 @@ pw_gemm_tf32x3_kernel(const PwParams p) {
       for (int j = 0; j < 4; ++j) {
         const float* bp = &Ws[buf][ks + t][wc + j * 8 + g];
         split_tf32(bp[0], bh[j][0], bl[j][0]);
-        split_tf32(bp[4 * kTWPitch], bh[j][1], bl[j][1]);
+        split_tf32(bp[4 * WPitch], bh[j][1], bl[j][1]);
       }
       // term-major order: 8 independent MMAs between two that share an accumulator; column
       // fragments beyond Nc (warp-uniform) are skipped
@@ -478,7 +482,7 @@ pw_gemm_tf32x3_kernel(const PwParams p) {
         for (int j = 0; j < 4; ++j) {
           if (n0 + wc + j * 8 >= p.Nc) continue;
 #pragma unroll
-          for (int i = 0; i < 2; ++i) mma_tf32(acc[i][j], term == 0 ? al[i] : ah[i], term == 1 ? bl[j] : bh[j]);
+          for (int i = 0; i < MF; ++i) mma_tf32(acc[i][j], term == 0 ? al[i] : ah[i], term == 1 ? bl[j] : bh[j]);
         }
     }
     if (kt + 1 < nk) stage(buf ^ 1);                 // last read before the barrier that ended kt-1
@@ -494,7 +498,7 @@ pw_gemm_tf32x3_kernel(const PwParams p) {
     float2 bv = make_float2(0.f, 0.f);
     if (p.bias) bv = __ldg(reinterpret_cast<const float2*>(p.bias + col));
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < MF; ++i)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const long m = m0 + wm + i * 16 + g + h * 8;
@@ -671,7 +675,14 @@ int x3d_pw_fwd(const x3d_pw_args* a, void* stream) {
   dim3 grid((unsigned)mt, (a->Nc + kBN - 1) / kBN);
   cudaStream_t st = S(stream);
   if (a->a_dtype == X3D_F32 && a->d_dtype == X3D_F32)
-    pw_gemm_tf32x3_kernel<<<grid, 256, 0, st>>>(p);
+  {
+    if (a->Nc <= 32) {
+      grid.y = 1;
+      pw_gemm_tf32x3_kernel<32><<<grid, 256, 0, st>>>(p);
+    } else {
+      pw_gemm_tf32x3_kernel<64><<<grid, 256, 0, st>>>(p);
+    }
+  }
   else if (a->a_dtype == X3D_BF16 && a->d_dtype == X3D_BF16)
     pw_gemm_kernel<bf16, bf16, true><<<grid, 256, 0, st>>>(p);
   else if (a->a_dtype == X3D_BF16 && a->d_dtype == X3D_F32)
