@@ -883,6 +883,128 @@ static inline unsigned ew_blocks(long n) {
 }  // namespace x3d
 
 using namespace x3d;
+namespace x3d {
+namespace train {
+// Backward-filter of the stem's temporal conv as a stream over (pixel, channel quad) columns: a thread
+// walks the T frames of its column with the KT s-values of the window in registers, so s and dy are
+// each read once with 128-bit loads (the kernel above re-reads s KT times with 4-byte loads and 24 of
+// 32 lanes busy at C = 24).  The block size is a multiple of C/4, a thread keeps its channel quad;
+// per-thread fp32 sums are combined in fixed order in shared memory, fp64 atomics per block.
+template <int KT>
+__global__ void __launch_bounds__(256)
+tconv_wgrad_vec_kernel(const float4* __restrict__ s, const float4* __restrict__ dy, double* __restrict__ dwt, int T,
+                       long PC4, int C4, long ncols) {
+  __shared__ float4 sh[KT][256];
+  const int tid = threadIdx.x, bs = blockDim.x;
+  float4 acc[KT];
+#pragma unroll
+  for (int d = 0; d < KT; ++d) acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long stride = (long)gridDim.x * bs;
+  for (long col = (long)blockIdx.x * bs + tid; col < ncols; col += stride) {
+    const long n = col / PC4, rem = col - n * PC4;
+    const float4* sp = s + n * T * PC4 + rem;
+    const float4* gp = dy + n * T * PC4 + rem;
+    float4 w[KT];                                         // w[d] = s[t + d - KT/2], zero outside the clip
+#pragma unroll
+    for (int d = 0; d < KT; ++d) {
+      const int ti = d - KT / 2;
+      w[d] = (ti >= 0 && ti < T) ? __ldg(sp + ti * PC4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int t = 0; t < T; ++t) {
+      const float4 g = __ldg(gp + t * PC4);
+      const int tn = t + 1 + KT / 2;
+      const float4 nx = tn < T ? __ldg(sp + tn * PC4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int d = 0; d < KT; ++d) {
+        acc[d].x = fmaf(w[d].x, g.x, acc[d].x); acc[d].y = fmaf(w[d].y, g.y, acc[d].y);
+        acc[d].z = fmaf(w[d].z, g.z, acc[d].z); acc[d].w = fmaf(w[d].w, g.w, acc[d].w);
+      }
+#pragma unroll
+      for (int d = 0; d + 1 < KT; ++d) w[d] = w[d + 1];
+      w[KT - 1] = nx;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < KT; ++d) sh[d][tid] = acc[d];
+  __syncthreads();
+  const int C = C4 * 4;
+  for (int e = tid; e < KT * C4; e += bs) {
+    const int d = e / C4, c4 = e - d * C4;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    for (int g = c4; g < bs; g += C4) {
+      const float4 v = sh[d][g];
+      t0 += v.x; t1 += v.y; t2 += v.z; t3 += v.w;
+    }
+    double* o = dwt + (long)d * C + c4 * 4;
+    atomicAdd(o, t0); atomicAdd(o + 1, t1); atomicAdd(o + 2, t2); atomicAdd(o + 3, t3);
+  }
+}
+}  // namespace train
+}  // namespace x3d
+
+namespace x3d {
+namespace train {
+// Backward-filter of the stem's spatial conv, one thread per (output pixel, channel quad): the 27 input
+// values of the pixel's window meet a 128-bit load of ds, 108 FMAs per 28 loads, all lanes busy for any
+// C % 4 == 0 (the kernel above keeps a warp on 32 channels of one pixel: 24 of 32 lanes at C = 24 and
+// one FMA per load).  Block size a multiple of C/4; the 27 x 4 per-thread sums are combined through
+// shared memory in three passes of 9 taps, fixed order, fp64 atomics per block.
+__global__ void __launch_bounds__(256)
+stem_convs_wgrad_vec_kernel(const float* __restrict__ in, const float4* __restrict__ ds, double* __restrict__ dws,
+                            int H, int W, int Ho, int Wo, int C4, int opix) {
+  __shared__ float4 sh[9][256];
+  const int tid = threadIdx.x, bs = blockDim.x, ppb = bs / C4;
+  const int c4 = tid % C4, pl = tid / C4;
+  float4 acc[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = blockIdx.x * ppb + pl; p < opix; p += gridDim.x * ppb) {
+    const int wo = p % Wo, q = p / Wo;
+    const int ho = q % Ho, nt = q / Ho;
+    const float4 g = __ldg(ds + (long)p * C4 + c4);
+    const int hi0 = 2 * ho - 1, wi0 = 2 * wo - 1;
+    const float* base = in + ((long)nt * H * W) * 3;
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int hi = hi0 + dh;
+      const bool rok = hi >= 0 && hi < H;
+      const float* row = base + ((long)(rok ? hi : 0) * W) * 3;
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int wi = wi0 + dw;
+        const bool ok = rok && wi >= 0 && wi < W;
+        const float* px = row + (ok ? wi : 0) * 3;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float v = ok ? __ldg(px + ci) : 0.f;
+          float4& a = acc[(dh * 3 + dw) * 3 + ci];
+          a.x = fmaf(v, g.x, a.x); a.y = fmaf(v, g.y, a.y); a.z = fmaf(v, g.z, a.z); a.w = fmaf(v, g.w, a.w);
+        }
+      }
+    }
+  }
+  const int C = C4 * 4;
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sh[k][tid] = acc[pass * 9 + k];
+    __syncthreads();
+    for (int e = tid; e < 9 * C4; e += bs) {
+      const int k = e / C4, cc = e - k * C4;
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+      for (int gidx = cc; gidx < ppb * C4; gidx += C4) {
+        const float4 v = sh[k][gidx];
+        t0 += v.x; t1 += v.y; t2 += v.z; t3 += v.w;
+      }
+      double* o = dws + (long)(pass * 9 + k) * C + cc * 4;
+      atomicAdd(o, t0); atomicAdd(o + 1, t1); atomicAdd(o + 2, t2); atomicAdd(o + 3, t3);
+    }
+    __syncthreads();
+  }
+}
+}  // namespace train
+}  // namespace x3d
+
 using namespace x3d::train;
 
 extern "C" {
@@ -1026,6 +1148,14 @@ int x3d_stem_convs_wgrad(const float* in, const float* ds, double* dws, int N, i
   long ppb = 1024;
   long yb = (opix + ppb - 1) / ppb;
   if (yb > 65535) { ppb = (opix + 65534) / 65535; yb = (opix + ppb - 1) / ppb; }
+  if (C % 4 == 0 && C / 4 <= 64 && opix < (1L << 31) && (reinterpret_cast<uintptr_t>(ds) & 15) == 0) {
+    const int C4 = C / 4, bs = 256 / C4 * C4, per = bs / C4;
+    long blocks = (opix + per - 1) / per;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    train::stem_convs_wgrad_vec_kernel<<<(unsigned)blocks, bs, 0, S(stream)>>>(
+        in, reinterpret_cast<const float4*>(ds), dws, H, W, Ho, Wo, C4, (int)opix);
+    return check_launch("x3d_stem_convs_wgrad");
+  }
   dim3 grid((C + 31) / 32, (unsigned)yb);
   stem_convs_wgrad_kernel<<<grid, 256, 0, S(stream)>>>(in, ds, dws, H, W, Ho, Wo, C, opix, ppb);
   return check_launch("x3d_stem_convs_wgrad");
@@ -1047,6 +1177,16 @@ int x3d_tconv_wgrad(const float* s, const float* dy, double* dwt, int N, int T, 
   long rpb = 1024;
   long yb = (rows + rpb - 1) / rpb;
   if (yb > 65535) { rpb = (rows + 65534) / 65535; yb = (rows + rpb - 1) / rpb; }
+  if (kt == 5 && C % 4 == 0 && C / 4 <= 256 &&
+      ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0) {
+    const int C4 = C / 4, bs = 256 / C4 * C4;
+    const long PC4 = P * C4, ncols = (long)N * PC4;
+    long blocks = (ncols + bs - 1) / bs;
+    if (blocks > 148L * 8) blocks = 148L * 8;
+    tconv_wgrad_vec_kernel<5><<<(unsigned)blocks, bs, 0, S(stream)>>>(
+        reinterpret_cast<const float4*>(s), reinterpret_cast<const float4*>(dy), dwt, T, PC4, C4, ncols);
+    return check_launch("x3d_tconv_wgrad");
+  }
   dim3 grid((C + 31) / 32, (unsigned)yb);
   tconv_wgrad_kernel<<<grid, 256, 0, S(stream)>>>(s, dy, dwt, T, P, C, kt, rows, rpb);
   return check_launch("x3d_tconv_wgrad");
