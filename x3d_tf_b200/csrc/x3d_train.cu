@@ -1005,6 +1005,52 @@ stem_convs_wgrad_vec_kernel(const float* __restrict__ in, const float4* __restri
 }  // namespace train
 }  // namespace x3d
 
+namespace x3d {
+namespace train {
+// Backward of swish(y * s) as a 128-bit stream per clip: block size a multiple of C/4, a thread keeps
+// its channel quad while it strides through the clip's [rows, C/4] float4 matrix; the per-clip sums
+// for the SE scale's gradient are combined in shared memory in fixed order, fp64 atomics per block.
+__global__ void __launch_bounds__(256)
+scale_swish_bwd_vec_kernel(const float4* __restrict__ dout, const float4* __restrict__ y, const float* __restrict__ s,
+                           float4* __restrict__ dy, double* __restrict__ ds, int C4, long clip4) {
+  __shared__ float4 sh[256];
+  const int tid = threadIdx.x, bs = blockDim.x, c4 = tid % C4;
+  const long n = blockIdx.y, base = n * clip4;
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (s) sc = __ldg(reinterpret_cast<const float4*>(s + n * C4 * 4) + c4);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long stride = (long)gridDim.x * bs;
+#pragma unroll 2
+  for (long i = (long)blockIdx.x * bs + tid; i < clip4; i += stride) {
+    const float4 yv = __ldg(y + base + i), g = __ldg(dout + base + i);
+    float4 o;
+#define X3D_SSB(f)                                                     \
+    {                                                                  \
+      const float v = yv.f * sc.f, sg = sigm(v);                       \
+      const float dv = g.f * (sg * (1.f + v * (1.f - sg)));            \
+      o.f = dv * sc.f;                                                 \
+      acc.f = fmaf(dv, yv.f, acc.f);                                   \
+    }
+    X3D_SSB(x) X3D_SSB(y) X3D_SSB(z) X3D_SSB(w)
+#undef X3D_SSB
+    dy[base + i] = o;
+  }
+  if (ds == nullptr) return;
+  sh[tid] = acc;
+  __syncthreads();
+  if (tid < C4) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    for (int gi = tid; gi < bs; gi += C4) {
+      const float4 v = sh[gi];
+      t0 += v.x; t1 += v.y; t2 += v.z; t3 += v.w;
+    }
+    double* o = ds + n * C4 * 4 + tid * 4;
+    atomicAdd(o, t0); atomicAdd(o + 1, t1); atomicAdd(o + 2, t2); atomicAdd(o + 3, t3);
+  }
+}
+}  // namespace train
+}  // namespace x3d
+
 using namespace x3d::train;
 
 extern "C" {
@@ -1214,6 +1260,20 @@ int x3d_scale_swish_bwd(const float* dout, const float* y, const float* s, float
   X3D_REQUIRE((s == nullptr) == (ds == nullptr), X3D_ERR_INVALID_ARG, "x3d_scale_swish_bwd: s and ds go together");
   const long clips = M / rows_per_clip, rb = (rows_per_clip + kRowsPerBlock - 1) / kRowsPerBlock;
   X3D_REQUIRE(clips <= 65535 && rb <= 65535, X3D_ERR_UNSUPPORTED, "x3d_scale_swish_bwd: too many clips / row blocks");
+  if (C % 4 == 0 && C / 4 <= 256 && clips <= 65535 &&
+      ((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) |
+        reinterpret_cast<uintptr_t>(s)) & 15) == 0) {
+    const int C4 = C / 4, bs = 256 / C4 * C4;
+    const long clip4 = rows_per_clip * C4;
+    long bx = (148L * 8 + clips - 1) / clips;              // ~8 CTAs per SM over all clips
+    const long need = (clip4 + bs - 1) / bs;
+    if (bx > need) bx = need;
+    if (bx < 1) bx = 1;
+    scale_swish_bwd_vec_kernel<<<dim3((unsigned)bx, (unsigned)clips), bs, 0, S(stream)>>>(
+        reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(y), s,
+        reinterpret_cast<float4*>(dy), ds, C4, clip4);
+    return check_launch("x3d_scale_swish_bwd");
+  }
   dim3 grid((C + 31) / 32, (unsigned)rb, (unsigned)clips);
   scale_swish_bwd_kernel<<<grid, 256, 0, S(stream)>>>(dout, y, s, dy, ds, C, rows_per_clip);
   return check_launch("x3d_scale_swish_bwd");
