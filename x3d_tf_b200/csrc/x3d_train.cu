@@ -1051,6 +1051,91 @@ scale_swish_bwd_vec_kernel(const float4* __restrict__ dout, const float4* __rest
 }  // namespace train
 }  // namespace x3d
 
+namespace x3d {
+namespace train {
+// Channelwise backward-filter, stride 1, two channels per thread: block size a multiple of C/2, thread
+// t owns channel pair t % (C/2) and row lane t / (C/2).  Per step of U = 4 output pixels the nine
+// (dt, dh) input rows are visited one after the other: six 64-bit loads (clamped offsets, zero select)
+// and 24 FMA pairs each, i.e. 3.7 FMAs per load against 1.9 in the one-channel kernel, with all lanes
+// busy for any even C.  The 27 x 2 sums per thread are combined through shared memory in three
+// passes of nine taps, fixed order; fp64 atomics per block.
+__global__ void __launch_bounds__(256, 2)
+dw_wgrad_pair_kernel(const float2* __restrict__ x, const float2* __restrict__ dy, double* __restrict__ dwt, int T,
+                     int H, int W, int C2, int ph, int pw, int orows, int rows_per_block) {
+  constexpr int U = 4, NC = U + 2;
+  __shared__ float2 sh[9][256];
+  const int tid = threadIdx.x, bs = blockDim.x;
+  const int c2 = tid % C2, rl = tid / C2, RL = bs / C2;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, orows);
+  float2 acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = make_float2(0.f, 0.f);
+  for (int row = r0 + rl; row < r1; row += RL) {
+    const int ho = row % H, q = row / H;
+    const int t = q % T, n = q / T;
+    int src[9];                                           // float2 index of (row, column 0, c2); -1 = padding
+#pragma unroll
+    for (int dt = 0; dt < 3; ++dt)
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh) {
+        const int ti = t + dt - 1, hi = ho + dh - ph;
+        src[dt * 3 + dh] = (ti >= 0 && ti < T && hi >= 0 && hi < H) ? (((n * T + ti) * H + hi) * W) * C2 + c2 : -1;
+      }
+    const float2* g = dy + (long)row * W * C2 + c2;
+    for (int wo0 = 0; wo0 < W; wo0 += U) {
+      int off[NC];
+      bool ok[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int wi = wo0 - pw + j;
+        ok[j] = wi >= 0 && wi < W;
+        off[j] = min(max(wi, 0), W - 1) * C2;
+      }
+      float2 gv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) gv[u] = (wo0 + u < W) ? __ldg(g + (wo0 + u) * C2) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        if (src[k] < 0) continue;                         // whole input row is padding
+        float2 xv[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          const float2 v = __ldg(x + src[k] + off[j]);
+          xv[j] = ok[j] ? v : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw) {
+            acc[k * 3 + dw].x = fmaf(xv[u + dw].x, gv[u].x, acc[k * 3 + dw].x);
+            acc[k * 3 + dw].y = fmaf(xv[u + dw].y, gv[u].y, acc[k * 3 + dw].y);
+          }
+      }
+    }
+  }
+  const int C = C2 * 2;
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sh[k][tid] = acc[pass * 9 + k];
+    __syncthreads();
+    for (int e = tid; e < 9 * C2; e += bs) {
+      const int k = e / C2, cc = e - k * C2;
+      double t0 = 0.0, t1 = 0.0;
+      for (int gi = cc; gi < RL * C2; gi += C2) {
+        const float2 v = sh[k][gi];
+        t0 += v.x; t1 += v.y;
+      }
+      double* o = dwt + (long)(pass * 9 + k) * C + cc * 2;
+      atomicAdd(o, t0); atomicAdd(o + 1, t1);
+    }
+    __syncthreads();
+  }
+}
+}  // namespace train
+}  // namespace x3d
+
 using namespace x3d::train;
 
 extern "C" {
@@ -1168,7 +1253,17 @@ int x3d_dw_wgrad(const float* x, const float* dy, double* dwt, int N, int T, int
   long yb = (orows + rpb - 1) / rpb;
   if (yb > 65535) { rpb = ((orows + 65534) / 65535 + 7) / 8 * 8; yb = (orows + rpb - 1) / rpb; }
   dim3 grid(cb, (unsigned)yb);
-  if (stride == 1)
+  if (stride == 1 && C % 2 == 0 && C / 2 <= 256 && (long)N * T * H * W * C < (1L << 31) &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 7) == 0) {
+    const int C2 = C / 2, bs = 256 / C2 * C2, RL = bs / C2;
+    long rp = (orows + 148L * 8 - 1) / (148L * 8);         // ~8 blocks per SM in total
+    if (rp < 2L * RL) rp = 2L * RL;
+    rp = (rp + RL - 1) / RL * RL;
+    const long nb = (orows + rp - 1) / rp;
+    train::dw_wgrad_pair_kernel<<<(unsigned)nb, bs, 0, S(stream)>>>(
+        reinterpret_cast<const float2*>(x), reinterpret_cast<const float2*>(dy), dwt, T, H, W, C2, pad_h, pad_w,
+        (int)orows, (int)rp);
+  } else if (stride == 1)
     train::dw_wgrad_kernel<1, 4><<<grid, 256, 0, S(stream)>>>(x, dy, dwt, T, H, W, Ho, Wo, C, pad_h, pad_w, orows, rpb);
   else {                                                   // measured: 2.3 ms (slide) against 3.1 ms (batched, U = 2) per step
     long rs = 16, ys = (orows + rs - 1) / rs;
