@@ -227,7 +227,7 @@ class PointwiseConv:
         for P in (4, 2):
             if P > Options.pair_pixels or M % P or (rows_per_clip and rows_per_clip % P):
                 continue
-            if P * self.Ks > Options.pair_max_k or P * self.Ns > 256:
+            if P * self.Ks > Options.pair_max_k or P * self.Ns > Options.pair_max_n:
                 continue
             if not Options.pair_aligned and self.Ks % 16 == 0 and self.Ns % 16 == 0:
                 continue
@@ -286,9 +286,11 @@ class Options:
     # pointwise convs whose rows are not a multiple of 32 bytes (24 / 56 channels): two pixels per GEMM
     # row with a block-diagonal weight (PointwiseConv).  Measured at 80 clips of 16x256^2 (step, a,
     # shortcut in ms): off 11.66 / 2.95 / 0.52; factor 2 10.97 / 2.47 / 0.37; factor 4 11.07; factor 2
-    # also on sector-aligned rows (X3D_PAIR_ALIGNED=1) 11.23.  X3D_PAIR_PIXELS=1 turns it off.
+    # also on sector-aligned rows (X3D_PAIR_ALIGNED=1) 11.23; pairing the 432-byte rows of stage 4 as
+    # well (X3D_PAIR_MAX_N=512, two N tiles) 11.03 against 10.94.  X3D_PAIR_PIXELS=1 turns it off.
     pair_pixels = int(os.environ.get("X3D_PAIR_PIXELS", "2"))       # largest pairing factor (1 = off, 2, 4)
     pair_max_k = int(os.environ.get("X3D_PAIR_MAX_K", "256"))
+    pair_max_n = int(os.environ.get("X3D_PAIR_MAX_N", "256"))
     pair_aligned = os.environ.get("X3D_PAIR_ALIGNED", "0") == "1"   # also pair rows that are sector-aligned
 
 
