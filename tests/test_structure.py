@@ -150,3 +150,42 @@ def test_training_lr_schedule_matches_train_py():
     assert lr_schedule(cfg, t.WARMUP_EPOCHS) == pytest.approx(t.BASE_LR)
     e = t.WARMUP_EPOCHS + 10
     assert lr_schedule(cfg, e) == pytest.approx(t.BASE_LR * 0.5 * (math.cos(math.pi * e / t.EPOCHS) + 1))
+
+
+def test_pixel_pairing_host_logic():
+    """PointwiseConv's pixel pairing (host side, no kernel call): which layers are paired, that pairs
+    never straddle clips, and that the paired weight is blockdiag(W, ..., W) of the BN-folded kernel in
+    the packed [Npad, Kpad] layout with the bias repeated per pixel slot."""
+    import numpy as np
+    import torch
+    from x3d_tf_b200 import model as M
+    rng = np.random.default_rng(3)
+    saved = (M.Options.pair_pixels, M.Options.pair_aligned, M.Options.pair_max_k, M.Options.pair_max_n)
+    try:
+        M.Options.pair_pixels, M.Options.pair_aligned, M.Options.pair_max_k, M.Options.pair_max_n = 2, False, 256, 256
+        cpu = torch.device("cpu")
+        mk = lambda K, N: M.PointwiseConv(rng.normal(size=(1, 1, 1, K, N)).astype(np.float32),
+                                          rng.uniform(0.5, 1.5, N), rng.normal(size=N), cpu)
+        a2, c2, a3, a4 = mk(24, 54), mk(54, 24), mk(48, 108), mk(96, 216)
+        assert a2._pair_factor(1000) == 2 and c2._pair_factor(1000) == 2     # 48- / 112-byte rows
+        assert a3._pair_factor(1000) == 1                                    # 96 / 224 bytes: sector-aligned
+        assert a4._pair_factor(1000) == 1                                    # 2 * 216 > one MMA tile
+        assert a2._pair_factor(1001) == 1                                    # odd row count
+        assert a2._pair_factor(2 * 13 * 91 * 91, 13 * 91 * 91) == 1          # odd clip: a pair would straddle clips
+        assert a2._pair_factor(2 * 16 * 64 * 64, 16 * 64 * 64) == 2
+        M.Options.pair_pixels = 4
+        assert a2._pair_factor(1000) == 4 and a2._pair_factor(1002) == 2
+        M.Options.pair_pixels = 1
+        assert a2._pair_factor(1000) == 1
+        M.Options.pair_aligned, M.Options.pair_pixels = True, 2
+        assert a3._pair_factor(1000) == 2
+        wp, bias = a2._paired_weights(2, cpu)
+        Ks, Ns = a2.Ks, a2.Ns
+        assert wp.shape == ((2 * Ns + 15) // 16 * 16, (2 * Ks + 63) // 64 * 64) and wp.dtype == torch.bfloat16
+        w = wp.float().numpy()
+        single = a2.wp.float().numpy()[:Ns, :Ks]
+        assert np.array_equal(w[:Ns, :Ks], single) and np.array_equal(w[Ns:2 * Ns, Ks:2 * Ks], single)
+        assert not w[:Ns, Ks:].any() and not w[Ns:2 * Ns, :Ks].any() and not w[2 * Ns:].any()
+        assert torch.equal(bias, torch.cat([a2.bias, a2.bias]))
+    finally:
+        M.Options.pair_pixels, M.Options.pair_aligned, M.Options.pair_max_k, M.Options.pair_max_n = saved
