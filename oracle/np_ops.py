@@ -75,3 +75,23 @@ def pointwise_conv_valid(x: np.ndarray, kernel: np.ndarray, stride: int = 1) -> 
     """x [N,T,H,W,Ci]; kernel [1,1,1,Ci,Co]; stride on H and W, 'valid'."""
     xs = x.astype(np.float64)[:, :, ::stride, ::stride, :]
     return xs @ kernel[0, 0, 0].astype(np.float64)
+
+
+def tf32x3_matmul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Arithmetic model of the 3xTF32 pointwise GEMM (x3d_tf_b200/csrc/x3d_simt.cu: split_tf32 +
+    mma.sync.m16n8k8.tf32; used for the fp32 pointwise convs, reference model.py:246-258,292-303):
+    every fp32 operand is split into hi = x rounded to TF32 (10 mantissa bits, half away from zero,
+    integer add + mask) and lo = x - hi (exact in fp32) pre-biased by half a TF32 ulp and truncated to
+    TF32 as the tensor core does with the low 13 bits; the product is lo.hi + hi.lo + hi.hi.  The sums
+    are taken in float64 here, so the result isolates the error of the SPLIT (the dropped lo.lo term
+    and the rounding of lo); the kernel's fp32 accumulation adds ordinary fp32 rounding on top."""
+    def split(x):
+        x = np.ascontiguousarray(x, np.float32)
+        bits = x.view(np.uint32)
+        hi = ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+        lo = (x - hi).astype(np.float32)
+        lo_t = ((lo.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+        return hi.astype(np.float64), lo_t.astype(np.float64)
+    ah, al = split(a)
+    bh, bl = split(b)
+    return al @ bh + ah @ bl + ah @ bh

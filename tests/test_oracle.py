@@ -87,3 +87,29 @@ def test_se_taps_only_on_se_blocks():
     se = sorted(k for k in taps if k.endswith("/se_scale"))
     assert len(se) == 13
     assert se[0] == "stages/0/stage/layer_with_weights-0/bottleneck/se_scale"
+
+
+def test_tf32x3_split_keeps_fp32_accuracy():
+    """The 3xTF32 split behind x3d_pw_fwd / x3d_pw_wgrad (fp32): the arithmetic model in np_ops bounds
+    its error at ~2^-21 of |a|.|b| per product (lo.lo dropped, lo rounded to TF32), i.e. below the
+    rounding of an fp32 GEMM of the layer shapes; a plain TF32 product (hi.hi only) is ~1000x worse,
+    which is why the single-MMA form cannot hold the 1e-4 logit bound of the fp32 path."""
+    from oracle import np_ops
+    rng = np.random.default_rng(0)
+    for K, N in ((24, 56), (216, 96), (432, 192)):
+        a = rng.normal(size=(256, K)).astype(np.float32)
+        b = (rng.normal(size=(K, N)) * 0.1).astype(np.float32)
+        want = a.astype(np.float64) @ b.astype(np.float64)
+        scale = np.abs(want).max()
+        err3 = np.abs(np_ops.tf32x3_matmul(a, b) - want).max() / scale
+        fp32 = np.abs((a @ b).astype(np.float64) - want).max() / scale
+        hi = lambda x: ((x.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32).astype(np.float64)
+        err1 = np.abs(hi(a) @ hi(b) - want).max() / scale
+        assert err3 < 2e-6 and err3 < 4 * max(fp32, 1e-7), (K, N, err3, fp32)
+        assert err1 > 50 * err3, (K, N, err1, err3)
+    # exactness of the split itself: hi + lo == x, hi has 10 mantissa bits
+    x = rng.normal(size=4096).astype(np.float32)
+    bits = x.view(np.uint32)
+    h = ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    assert np.array_equal((h.astype(np.float64) + (x - h).astype(np.float64)).astype(np.float32), x)
+    assert not (h.view(np.uint32) & np.uint32(0x1FFF)).any()
