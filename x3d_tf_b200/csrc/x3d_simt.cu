@@ -1,6 +1,7 @@
 // CUDA-core (SIMT) kernels of the X3D forward path for sm_100a:
-//   stem (fused conv_s + conv_t + BN + ReLU), SE MLP, global average pool, softmax + view mean, and the generic fp32-accumulate pointwise
-//   GEMM used by the fp32 path, the strided shortcut conv and the head.
+//   stem (fused conv_s + conv_t + BN + ReLU), SE MLP, global average pool, softmax + view mean, and the generic pointwise
+//   GEMM behind x3d_pw_fwd: fp32 activations (fp32 path, training step) on the tensor cores with the 3xTF32 split
+//   (pw_gemm_tf32x3_kernel), bf16 activations without the tcgen05 path's layout requirements on CUDA cores (pw_gemm_kernel).
 // The bf16 tensor-core pointwise GEMM lives in x3d_pw_tc.cu, the channelwise stencil in x3d_dw_tma.cu.
 #include "common.cuh"
 
