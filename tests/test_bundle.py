@@ -141,9 +141,46 @@ def test_train_driver_host_logic(tmp_path):
     for i in range(5):
         np.save(tmp_path / f"c{i}.npy", np.full((2, 1, 2, 2, 3) if i % 2 else (1, 2, 2, 3), i, np.uint8))
         items.append((str(tmp_path / f"c{i}.npy"), i))
-    batches = list(T.file_clip_batches(items, 2, np.random.default_rng(0)))
+    batches = list(T.file_clip_batches(items, 2, 2, seed=0))
     assert len(batches) == 2 and all(b[0].shape == (2, 1, 2, 2, 3) for b in batches)
     for clips, labels in batches:                          # the label travels with its clip
         assert [int(c.flat[0]) for c in clips] == labels.tolist()
-    syn = list(T.synthetic_clip_batches(5, 2, 1, 4, 400, 3))
+    syn = list(T.synthetic_clip_batches(2, 2, 1, 4, 400, 3))
     assert len(syn) == 2 and syn[0][0].dtype == np.uint8 and syn[0][1].dtype == np.int32
+    # Every rank runs the SAME number of steps whatever the list length (a 5-item list split over 2
+    # ranks used to give 3 / 2 items, i.e. different step counts and mismatched collectives), the
+    # ranks' slices of one global batch are disjoint, and a short list repeats (Keras steps_per_epoch).
+    per_rank = [list(T.file_clip_batches(items, 4, 3, seed=5, rank=r, world=2)) for r in range(2)]
+    assert [len(b) for b in per_rank] == [3, 3]
+    idx = list(T.global_batch_indices(5, 4, 3, seed=5))
+    assert all(len(set(i.tolist())) == 4 for i in idx[:1]) and sum(len(i) for i in idx) == 12
+    for step in range(3):
+        l0, l1 = per_rank[0][step][1].tolist(), per_rank[1][step][1].tolist()
+        assert l0 + l1 == idx[step].tolist()
+
+
+def test_from_scratch_init_is_keras_default():
+    """train.py:128 builds `X3D(cfg)` with Keras default initialisers: BN gamma=1, beta=0, mean=0,
+    variance=1, zero biases, Glorot-uniform kernels with `_compute_fans` of the kernel tensor
+    (a channelwise (3,3,3,1,C) kernel: fan_in 27, fan_out 27*C)."""
+    from x3d_tf_b200.config import get_config
+    from x3d_tf_b200.model import keras_default_weights
+    W = keras_default_weights(get_config("X3D_M"), seed=1111)
+    assert len(W) == 476
+    for k, v in W.items():
+        leaf = k.rsplit("/", 1)[1]
+        if leaf in ("gamma", "moving_variance"):
+            assert np.all(v == 1.0), k
+        elif leaf in ("beta", "moving_mean", "bias"):
+            assert np.all(v == 0.0), k
+        else:
+            shp = v.shape
+            rf = int(np.prod(shp[:-2])) if len(shp) == 5 else 1
+            lim = np.sqrt(6.0 / (rf * shp[-2] + rf * shp[-1]))
+            assert np.abs(v).max() <= lim + 1e-7, k
+            if v.size > 500:
+                assert np.abs(v).max() > 0.9 * lim, k
+    b = W["stages/0/stage/layer_with_weights-0/bottleneck/b/kernel"]
+    assert b.shape == (3, 3, 3, 1, 54) and np.abs(b).max() <= np.sqrt(6.0 / (27 + 27 * 54)) + 1e-7
+    W2 = keras_default_weights(get_config("X3D_M"), seed=1111)
+    assert all(np.array_equal(W[k], W2[k]) for k in W)

@@ -22,6 +22,28 @@ int check_launch(const char* what);            // host_util.cpp: cudaGetLastErro
 
 using bf16 = __nv_bfloat16;
 
+// cudaFuncSetAttribute is a per-DEVICE setting: the opt-in shared-memory size a launcher has
+// configured is remembered per (kernel instance, device), so a second GPU driven from the same
+// process gets its own call (the C ABI allows one context per GPU in one process).
+constexpr int kMaxDevices = 64;
+struct SmemOptIn {
+  size_t configured[kMaxDevices] = {};
+};
+template <typename Kern>
+inline cudaError_t ensure_dynamic_smem(Kern kern, SmemOptIn& state, size_t bytes, bool max_carveout = true) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool tracked = dev >= 0 && dev < kMaxDevices;
+  if (tracked && bytes <= state.configured[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) return e;
+  if (max_carveout)
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (tracked) state.configured[dev] = bytes;
+  return cudaSuccess;
+}
+
 // ---- two-channel (the unit a channelwise thread owns) and vector loads/stores ----
 __device__ __forceinline__ float2 ld2(const float* p) {
   return __ldg(reinterpret_cast<const float2*>(p));

@@ -54,18 +54,26 @@ EncodeTiledFn tensor_map_encoder() {
   return fn;
 }
 
-static int g_sms = -1, g_smem = 0, g_major = 0;
-static void query_device() {
-  if (g_sms >= 0) return;
+// Properties of the CURRENT device, cached per device ordinal (one process may drive several GPUs).
+struct DevInfo { int sms = -1, smem = 0, major = 0; };
+static DevInfo g_dev[kMaxDevices];
+static const DevInfo& query_device() {
+  static const DevInfo none{0, 0, 0};
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) { g_sms = 0; return; }
-  cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&g_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  cudaDeviceGetAttribute(&g_major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return none;
+  DevInfo& d = g_dev[dev];
+  if (d.sms < 0) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&d.smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    d.sms = sms;
+  }
+  return d;
 }
-int device_sm_count() { query_device(); return g_sms; }
-int device_max_smem() { query_device(); return g_smem; }
-bool device_is_sm100() { query_device(); return g_major == 10; }
+int device_sm_count() { return query_device().sms; }
+int device_max_smem() { return query_device().smem; }
+bool device_is_sm100() { return query_device().major == 10; }
 
 }  // namespace x3d
 

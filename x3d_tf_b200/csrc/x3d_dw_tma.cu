@@ -301,17 +301,11 @@ static Plan make_plan(int H, int W, int Cs, int stride, int esize) {
 template <typename T, int S, int SW, int CH>
 static int launch(const CUtensorMap& tm, const CUtensorMap& tmo, const Params& p, const Plan& pl, int N, cudaStream_t st) {
   auto kern = dw_tma_kernel<T, S, SW, CH>;
-  static size_t configured = 0;
-  if (pl.smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)pl.smem);
-    if (e != cudaSuccess) {
-      set_error("x3d_dw3x3x3_fwd: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e));
-      return X3D_ERR_LAUNCH;
-    }
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         cudaSharedmemCarveoutMaxShared);
-    configured = pl.smem;
+  static SmemOptIn optin;                              // one per template instance, per device inside
+  const cudaError_t e = ensure_dynamic_smem(kern, optin, pl.smem);
+  if (e != cudaSuccess) {
+    set_error("x3d_dw3x3x3_fwd: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e));
+    return X3D_ERR_LAUNCH;
   }
   dim3 grid(pl.tiles_w * pl.tiles_h, pl.chunks, N);
   kern<<<grid, pl.threads, pl.smem, st>>>(tm, tmo, p);

@@ -514,12 +514,13 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool pro = (a->se != nullptr) || a->swish;
   cudaError_t e;
+  static SmemOptIn optin_pro, optin_plain;             // per device inside (the attribute is per device)
   if (pro) {
-    e = cudaFuncSetAttribute(tc::pw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dynamic_smem(tc::pw_tc_kernel<true>, optin_pro, smem, false);
     X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
     tc::pw_tc_kernel<true><<<grid, tc::kThreadsPro, smem, st>>>(tmA, tmW, tmD, p);
   } else {
-    e = cudaFuncSetAttribute(tc::pw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dynamic_smem(tc::pw_tc_kernel<false>, optin_plain, smem, false);
     X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
     tc::pw_tc_kernel<false><<<grid, tc::kThreadsPlain, smem, st>>>(tmA, tmW, tmD, p);
   }

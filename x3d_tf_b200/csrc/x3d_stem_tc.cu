@@ -370,14 +370,10 @@ static int stem_tc_launch_impl(const void* in, const void* wc, const float* bias
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   dim3 grid((Wo + stemtc::kTW - 1) / stemtc::kTW, (Ho + stemtc::kTH - 1) / stemtc::kTH, N);
   X3D_REQUIRE(grid.y <= 65535, X3D_ERR_UNSUPPORTED, "x3d_stem_tc_fwd: image too tall");
-  static bool configured = false;                   // one flag per template instance
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(stemtc::stem_tc_kernel<TI, kStaged>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)stemtc::kSmemBytes);
+  static SmemOptIn optin;                           // one per template instance, per device inside
+  {
+    const cudaError_t e = ensure_dynamic_smem(stemtc::stem_tc_kernel<TI, kStaged>, optin, stemtc::kSmemBytes);
     X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_stem_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
-    cudaFuncSetAttribute(stemtc::stem_tc_kernel<TI, kStaged>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         cudaSharedmemCarveoutMaxShared);
-    configured = true;
   }
   stemtc::stem_tc_kernel<TI, kStaged><<<grid, stemtc::kThreads, stemtc::kSmemBytes, st>>>(
       static_cast<const TI*>(in), static_cast<const uint4*>(wc), bias, static_cast<bf16*>(out), T, H, W, Ho, Wo,

@@ -77,8 +77,10 @@ class Layer:
         return np.random.default_rng(Layer._init_seed)
 
     def _add_conv(self, key: str, shape: Tuple[int, ...], groups: int = 1):
+        # Keras `_compute_fans`: receptive field x shape[-2] / x shape[-1] of the KERNEL tensor, so a
+        # channelwise (3,3,3,1,C) kernel has fan_in = 27 and fan_out = 27*C (groups play no part)
         rf = int(np.prod(shape[:-2]))
-        fan_in, fan_out = rf * shape[-2], rf * shape[-1] // groups
+        fan_in, fan_out = rf * shape[-2], rf * shape[-1]
         self._vars[key] = _glorot(self._rng(), shape, fan_in, fan_out)
 
     def _add_bn(self, key: str, c: int):
@@ -589,6 +591,19 @@ def finalize_metrics(acc: torch.Tensor, group=None, k: int = 5, return_dict: boo
     return res if return_dict else [res["loss"], res["acc"], res[f"top_{k}_acc"]]
 
 
+def keras_default_weights(cfg, seed: int = 0) -> "OrderedDict[str, np.ndarray]":
+    """The variables of a freshly constructed `X3D(cfg)` (train.py:128): Keras default initialisers,
+    seeded.  What a from-scratch training run starts from; `synth.synthetic_weights` (randomised BN
+    statistics and biases) is a parity/benchmark fixture only."""
+    saved = (ResBlock._block_index, ResStage._stage_index, Layer._init_seed)
+    reset_block_counters()
+    Layer._init_seed = int(seed) * 100003
+    try:
+        return X3D(cfg).named_variables()
+    finally:
+        ResBlock._block_index, ResStage._stage_index, Layer._init_seed = saved
+
+
 def reset_block_counters() -> None:
     """Back to the fresh-process state of the reference's class counters (model.py:326,401)."""
     ResBlock._block_index = 0
@@ -740,7 +755,12 @@ class X3D(Layer):
             self._graphs[key] = (g, static_in, s_probs, s_logits)
         return self._graphs[key]
 
-    def call(self, input, training: bool = False):
+    def __call__(self, x, training: bool = False, copy: bool = True):
+        return self.call(x, training=training, copy=copy)
+
+    def call(self, input, training: bool = False, copy: bool = True):
+        """`copy=False` returns the CUDA graph's static output buffers (valid until the next call
+        with the same input shape) instead of fresh tensors: the zero-allocation path bench.py times."""
         self._no_training(training)
         x = _as_device_clip(input, self._device)
         self._check_input(x.shape)
@@ -751,8 +771,13 @@ class X3D(Layer):
         if x.data_ptr() != static_in.data_ptr():
             static_in.copy_(x, non_blocking=True)
         g.replay()
-        self.last_logits = s_logits
-        return s_probs
+        if not copy:
+            # the captured graph's own output buffers: overwritten by the next call of this shape
+            self.last_logits = s_logits
+            return s_probs
+        # like a Keras call, every result is a tensor of its own (1.6 kB per video)
+        self.last_logits = s_logits.clone()
+        return s_probs.clone()
 
     def static_input(self, shape, dtype=torch.bfloat16):
         """The captured graph's input buffer for `shape` (fill it in place and pass it to

@@ -45,26 +45,44 @@ def epoch_of_checkpoint(path: str) -> int:
     return int(os.path.basename(path).split("-")[1])
 
 
-def file_clip_batches(items: List[Tuple[str, int]], batch: int, rng: np.random.Generator
-                      ) -> Iterator[Tuple[np.ndarray, np.ndarray]]:
-    """Shuffled batches of `batch` clips (one clip per listed file per epoch; a `[k,...]` file
+def global_batch_indices(n_items: int, gbatch: int, steps: int, seed: int) -> Iterator[np.ndarray]:
+    """Exactly `steps` global batches of `gbatch` item indices, identical on every rank (the seed
+    holds no rank): the list is reshuffled and repeated when it is shorter than `steps * gbatch`,
+    as Keras `fit(steps_per_epoch=...)` does on a repeating dataset.  Every rank therefore runs
+    the same number of steps whatever the list length -- the per-step gradient all-reduce of one
+    rank can never pair with another rank's end-of-epoch reduction."""
+    if n_items <= 0:
+        raise ValueError("empty training list")
+    rng = np.random.default_rng(seed)
+    pool = np.empty(0, np.int64)
+    for _ in range(steps):
+        while pool.size < gbatch:
+            pool = np.concatenate([pool, rng.permutation(n_items)])
+        yield pool[:gbatch]
+        pool = pool[gbatch:]
+
+
+def file_clip_batches(items: List[Tuple[str, int]], gbatch: int, steps: int, seed: int, rank: int = 0,
+                      world: int = 1) -> Iterator[Tuple[np.ndarray, np.ndarray]]:
+    """This rank's slice of every global batch (one clip per listed file; a `[k,...]` file
     contributes a random one of its k clips)."""
-    order = rng.permutation(len(items))
-    for i in range(0, len(order) - batch + 1, batch):
+    batch = gbatch // world
+    pick = np.random.default_rng(seed + 104729 * (rank + 1))
+    for idx in global_batch_indices(len(items), gbatch, steps, seed):
         clips, labels = [], []
-        for j in order[i:i + batch]:
+        for j in idx[rank * batch:(rank + 1) * batch]:
             a = np.load(items[j][0])
             if a.ndim == 5:
-                a = a[rng.integers(a.shape[0])]
+                a = a[pick.integers(a.shape[0])]
             clips.append(a)
             labels.append(items[j][1])
         yield np.stack(clips), np.asarray(labels, np.int32)
 
 
-def synthetic_clip_batches(n: int, batch: int, T: int, S: int, num_classes: int, seed: int
+def synthetic_clip_batches(steps: int, batch: int, T: int, S: int, num_classes: int, seed: int
                            ) -> Iterator[Tuple[np.ndarray, np.ndarray]]:
     rng = np.random.default_rng(seed)
-    for _ in range(n // batch):
+    for _ in range(steps):
         yield (rng.integers(0, 256, size=(batch, T, S, S, 3), dtype=np.uint8),
                rng.integers(0, num_classes, size=batch).astype(np.int32))
 
@@ -107,13 +125,14 @@ def run(argv: Optional[List[str]] = None) -> Optional[dict]:
 
     from . import ops
     from .arch import build_arch
-    from .model import X3D, reset_block_counters
-    from .synth import synthetic_weights
+    from .model import X3D, keras_default_weights, reset_block_counters
     from .training import X3DTrainer
     from .eval import file_batches
 
-    tr = X3DTrainer(cfg, device=dev, world=world)
-    tr.load(synthetic_weights(build_arch(cfg), seed=1111))           # Keras default initialisers, seeded
+    tr = X3DTrainer(cfg, device=dev, world=world, rank=rank)
+    # a from-scratch run starts where `X3D(cfg)` starts in the reference (train.py:128): Keras default
+    # initialisers -- Glorot-uniform kernels, zero biases, BN gamma=1 / beta=0 / mean=0 / variance=1
+    tr.load(keras_default_weights(cfg, seed=1111))
     current_epoch = 0
     ckpt = latest_checkpoint(a.model_dir)
     if ckpt:
@@ -133,7 +152,9 @@ def run(argv: Optional[List[str]] = None) -> Optional[dict]:
     epochs = a.epochs or cfg.TRAIN.EPOCHS
     steps = a.steps_per_epoch or max(cfg.TRAIN.DATASET_SIZE // gbatch, 1)
     T, S = cfg.DATA.TEMP_DURATION, a.crop_size or cfg.DATA.TRAIN_CROP_SIZE
-    items = read_file_list(a.train_file_pattern)[rank::world] if a.train_file_pattern else None
+    items = read_file_list(a.train_file_pattern) if a.train_file_pattern else None
+    if a.synthetic:
+        steps = min(steps, max(a.synthetic // gbatch, 1))
     val_items = read_file_list(a.val_file_pattern) if a.val_file_pattern else None
     mean, std = tuple(cfg.DATA.MEAN), tuple(cfg.DATA.STD)
     history = []
@@ -141,8 +162,9 @@ def run(argv: Optional[List[str]] = None) -> Optional[dict]:
         lr = lr_for_epoch(cfg, epoch)
         if rank == 0:
             print(f"\nEpoch {epoch + 1}/{epochs}\nEpoch {epoch + 1:05d}: LearningRateScheduler setting learning rate to {lr}.")
-        data = (file_clip_batches(items, batch, np.random.default_rng(1111 + 7919 * epoch + rank)) if items is not None
-                else synthetic_clip_batches(a.synthetic // world, batch, T, S, cfg.NETWORK.NUM_CLASSES,
+        # every rank runs exactly `steps` steps (rank-independent count; short lists repeat)
+        data = (file_clip_batches(items, gbatch, steps, 1111 + 7919 * epoch, rank, world) if items is not None
+                else synthetic_clip_batches(steps, batch, T, S, cfg.NETWORK.NUM_CLASSES,
                                             1111 + 7919 * epoch + rank))
         t0, n, loss_sum = time.time(), 0, torch.zeros((), dtype=torch.float64, device=dev)
         for clips, labels in data:

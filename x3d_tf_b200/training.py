@@ -53,11 +53,20 @@ class _Arena:
         return flat[off:off + int(np.prod(shape))].view(shape)
 
 
+def _mix64(z: int) -> int:
+    """splitmix64 finaliser (the same hash the dropout kernel applies per element)."""
+    z &= (1 << 64) - 1
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & ((1 << 64) - 1)
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & ((1 << 64) - 1)
+    return z ^ (z >> 31)
+
+
 class X3DTrainer:
     """`X3DTrainer(cfg).load(weights)`; `loss = trainer.step(clips, labels, lr)`."""
 
-    def __init__(self, cfg, device=None, world: int = 1, process_group=None, seed: int = 1111):
+    def __init__(self, cfg, device=None, world: int = 1, process_group=None, seed: int = 1111, rank: int = 0):
         self.cfg = cfg
+        self.rank = rank                    # mixed into the dropout stream: replicas draw independent masks
         self.arch = A.build_arch(cfg)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.world, self.pg = world, process_group
@@ -359,7 +368,7 @@ class X3DTrainer:
             else:
                 mask = torch.empty_like(h1)
                 check(L.x3d_dropout_mask(mask.data_ptr(), mask.numel(), self.dropout,
-                                         (self.seed << 20) + self.iteration, _s()), "x3d_dropout_mask")
+                                         self._dropout_seed(), _s()), "x3d_dropout_mask")
             hd = self._ew(h1, mask, 5)
             tape.append(lambda d, mask=mask: self._ew(d, mask, 5))
         else:
@@ -505,6 +514,12 @@ class X3DTrainer:
             return d                                     # continues into bn_c
         tape.append(join_bwd)
         return out.view(N, T, Ho, Wo, co)
+
+    def _dropout_seed(self) -> int:
+        """64-bit seed of this step's dropout stream: a hash of (seed, rank, iteration), so every
+        data-parallel replica draws its own mask (per-replica RNG under MirroredStrategy) and the
+        iteration counter never runs into the seed bits."""
+        return _mix64(_mix64(_mix64(self.seed) + self.rank) + self.iteration)
 
     def step(self, clips: torch.Tensor, labels: torch.Tensor, lr: float) -> torch.Tensor:
         """forward + backward + gradient all-reduce + SGD-Nesterov update.  Returns per-clip losses."""
