@@ -174,6 +174,19 @@ int x3d_expand_dw_fwd(const void* x, const void* wa, const float* bias_a, const 
                       int W, int Cin, int C, int Kpad, int Npad, int stride, int pad_h, int pad_w,
                       void* stream);
 
+/* Same layers (model.py:306-316), persistent warp-specialised form: one CTA per SM walks (clip,
+ * spatial tile) work items; TMA producer / tcgen05 issuer / TMEM drain warps / stencil warps / TMA
+ * store run decoupled through mbarrier rings.  The expand result is kept in fp32 on chip (it is
+ * NOT rounded to bf16 between the two convolutions, so the result is at least as close to the
+ * reference's fp32 arithmetic as the unfused pair's).  Arguments as x3d_expand_dw_fwd, plus
+ *   act  1: swish applied to the output (blocks without SE, model.py:316; se_partial must be NULL)
+ *   se_partial [N, nblk, C], nblk = x3d_expand_dw2_partial_blocks(...) (0: no tile plan fits). */
+int x3d_expand_dw2_partial_blocks(int T, int H, int W, int Cin, int C, int stride);
+int x3d_expand_dw2_fwd(const void* x, const void* wa, const float* bias_a, const float* wb,
+                       const float* bias_b, void* out, float* se_partial, int N, int T, int H,
+                       int W, int Cin, int C, int Kpad, int Npad, int stride, int pad_h, int pad_w,
+                       int act, void* stream);
+
 /* ==== Either side of the forward path ==================================
  * Input stage: utils.normalize, utils.py:42-72 (called from dataloader.py on decoded frames):
  *   out[p,c] = ((in[p,c] / norm_value) - mean[c]) / std[c]   in fp32, the reference's operation order.

@@ -246,12 +246,16 @@ def res_block(W, x, blk, spec, dtype, taps=None):
 
 def forward(W: Dict[str, np.ndarray], spec: OracleSpec, clips: np.ndarray,
             dtype=torch.float64, training: bool = False,
-            taps: Optional[dict] = None) -> Dict[str, np.ndarray]:
+            taps: Optional[dict] = None, channels_last: bool = False) -> Dict[str, np.ndarray]:
     """X3D.call (model.py:113-127) on NDHWC clips.  Returns logits (fc2 output, :121),
     per-clip softmax, and the view-averaged probabilities the reference returns (:123-127).
-    `taps`, when a dict, receives NCDHW intermediates keyed by layer for per-kernel parity."""
-    x = torch.from_numpy(np.ascontiguousarray(clips)).to(dtype).permute(0, 4, 1, 2, 3).contiguous()
-    with torch.no_grad():
+    `taps`, when a dict, receives NCDHW intermediates keyed by layer for per-kernel parity.
+    `channels_last`: keep the activations in torch's channels_last_3d memory format (the NDHWC
+    layout the reference computes in) -- same arithmetic, the timing protocol of BASELINE.md
+    section 3 for the CPU baseline."""
+    x = torch.from_numpy(np.ascontiguousarray(clips)).to(dtype).permute(0, 4, 1, 2, 3)
+    x = x.contiguous(memory_format=torch.channels_last_3d) if channels_last else x.contiguous()
+    with torch.inference_mode():
         out = stem(W, x, spec, dtype)                                     # :114
         if taps is not None:
             taps["conv1"] = out

@@ -153,6 +153,45 @@ def test_fused_expand_channelwise_tcgen05(N, T, H, W, Cin, C, stride):
     assert p2 is None and torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("N,T,H,W,Cin,C,stride", AB_CASES + [(3, 4, 20, 20, 24, 56, 1), (5, 2, 16, 16, 48, 112, 2),
+                                                            (2, 16, 64, 64, 24, 56, 1), (2, 7, 64, 64, 24, 56, 2)])
+def test_fused_expand_channelwise_persistent(N, T, H, W, Cin, C, stride):
+    """x3d_expand_dw2_fwd == relu(x.Wa + ta) (kept in fp32, NOT rounded to bf16) -> channelwise
+    conv (+ bias, + swish), i.e. model.py:306-316 with one rounding at the output; several clips so
+    that a CTA walks more than one work item."""
+    from x3d_tf_b200.arch import same_pad
+    ops = _ops()
+    if ops.expand_dw2_supported(T, H, W, Cin, C, stride) <= 0:
+        pytest.skip("no fused tile plan for this shape (the model falls back to the two kernels)")
+    rng = np.random.default_rng(H * 100 + W + C + stride + Cin)
+    x = bf16_round(rng.normal(size=(N, T, H, W, Cin)))
+    wa = bf16_round(rng.normal(size=(Cin, C)) / np.sqrt(Cin))
+    ta = rng.normal(size=C).astype(np.float32) * 0.3
+    k = rng.normal(size=(3, 3, 3, 1, C)).astype(np.float32) * 0.3
+    tb = rng.normal(size=C).astype(np.float32) * 0.2
+    a = np.maximum(x.reshape(-1, Cin).astype(np.float64) @ wa.astype(np.float64) + ta, 0.0)
+    want = np_ops.channelwise_conv_same(a.reshape(N, T, H, W, C), k, stride) + tb
+    npad, kpad = (C + 15) // 16 * 16, (Cin + 63) // 64 * 64
+    wp = np.zeros((npad, kpad), np.float32)
+    wp[:C, :Cin] = wa.T
+    _, ph, _ = same_pad(H, 3, stride)
+    _, pw, _ = same_pad(W, 3, stride)
+    args = (to_dev(x, torch.bfloat16), to_dev(wp, torch.bfloat16), to_dev(ta), to_dev(k.reshape(27, C)),
+            to_dev(tb), stride, ph, pw)
+    out, partial = ops.expand_dw2_fwd(*args, True)
+    torch.cuda.synchronize()
+    assert_close(to_np(out), want, torch.bfloat16, "persistent fused expand+channelwise")
+    sums = to_np(partial).astype(np.float64).sum(1)
+    np.testing.assert_allclose(sums, want.sum((1, 2, 3)), rtol=2e-4,
+                               atol=2e-4 * np.abs(want).sum((1, 2, 3)).max())
+    out2, p2 = ops.expand_dw2_fwd(*args, False)
+    assert p2 is None and torch.equal(out, out2)
+    out3, _ = ops.expand_dw2_fwd(*args, False, swish=True)
+    assert_close(to_np(out3), want / (1.0 + np.exp(-want)), torch.bfloat16, "persistent fused + swish")
+    with pytest.raises(ValueError):
+        ops.expand_dw2_fwd(*args, True, swish=True)
+
+
 # ------------------------------------------------------------------------------- pointwise
 def _pw_ref(a, w, bias, res=None, se=None, rpc=0, swish=False, relu=False):
     a = np.asarray(a, np.float64)

@@ -40,13 +40,16 @@ for si, (Hin, cin, inner, cout) in enumerate(stages):
             for se in (bool(a.se),):
                 timeit(f"dw s{si+2} {H}x{H}x{ci} stride{stride} se{int(se)}", lambda: ops.dw_fwd(x, w, b, stride, ph, ph, se),
                        (x.numel() + N * T * Ho * Ho * ci) * 2)
-        if a.what in ("ab", "all"):
+        if a.what in ("ab", "ab2", "all"):
             cin_s = pad8(cin if stride == 2 else cout)
             x = rnd(N, T, H, H, cin_s); w = rnd(27, ci, dtype=torch.float32); b = rnd(ci, dtype=torch.float32)
             wa = rnd((ci + 15) // 16 * 16, (cin_s + 63) // 64 * 64); ba = rnd(ci, dtype=torch.float32)
             _, ph, _ = same_pad(H, 3, stride)
-            if ops.expand_dw_supported(T, H, H, cin_s, ci, stride) > 0:
+            if a.what != "ab2" and ops.expand_dw_supported(T, H, H, cin_s, ci, stride) > 0:
                 timeit(f"ab s{si+2} {H}x{H} {cin_s}->{ci} stride{stride}", lambda: ops.expand_dw_fwd(x, wa, ba, w, b, stride, ph, ph, True),
+                       (x.numel() + N * T * Ho * Ho * ci) * 2)
+            if a.what in ("ab", "ab2", "all") and ops.expand_dw2_supported(T, H, H, cin_s, ci, stride) > 0:
+                timeit(f"ab2 s{si+2} {H}x{H} {cin_s}->{ci} stride{stride}", lambda: ops.expand_dw2_fwd(x, wa, ba, w, b, stride, ph, ph, bool(a.se)),
                        (x.numel() + N * T * Ho * Ho * ci) * 2)
             M = N * T * H * H
             timeit(f"  (a alone: M={M} K={cin_s} N={ci})", lambda: ops.pw_tc_fwd(x.view(M, cin_s), wa, ba, M=M, K=cin_s, Nc=ci, relu=True),

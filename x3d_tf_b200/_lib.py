@@ -68,6 +68,8 @@ SIGNATURES = {
                                       C.c_int, C.c_int, C.c_void_p]),
     "x3d_expand_dw_partial_blocks": (C.c_int, [C.c_int] * 6),
     "x3d_expand_dw_fwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 11 + [C.c_void_p]),
+    "x3d_expand_dw2_partial_blocks": (C.c_int, [C.c_int] * 6),
+    "x3d_expand_dw2_fwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 12 + [C.c_void_p]),
     # ---- training step
     "x3d_colreduce": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "x3d_bn_finalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float] + [C.c_void_p] * 6),

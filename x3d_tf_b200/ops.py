@@ -275,6 +275,39 @@ def expand_dw_fwd(x: torch.Tensor, wa: torch.Tensor, bias_a: torch.Tensor, wb: t
     return out, partial
 
 
+def expand_dw2_supported(T: int, H: int, W: int, cin: int, c: int, stride: int) -> int:
+    """SE partial blocks per clip of the persistent fused kernel's plan, 0 if no tile plan fits."""
+    return int(lib().x3d_expand_dw2_partial_blocks(T, H, W, cin, c, stride))
+
+
+def expand_dw2_fwd(x: torch.Tensor, wa: torch.Tensor, bias_a: torch.Tensor, wb: torch.Tensor,
+                   bias_b: torch.Tensor, stride: int, pad_h: int, pad_w: int, want_se: bool,
+                   swish: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Fused expand (1x1x1 + BN + ReLU) -> channelwise 3x3x3 (+ BN, SE sums or swish), persistent
+    warp-specialised kernel (x3d_expand_dw2_fwd); bf16 in / out, fp32 in between."""
+    _req(x, "x")
+    if x.dtype != torch.bfloat16:
+        raise TypeError("expand_dw2_fwd needs bf16 activations")
+    if swish and want_se:
+        raise ValueError("swish in the epilogue only without SE (the SE scale comes before the swish)")
+    N, T, H, W, cin = x.shape
+    C = wb.shape[1]
+    Ho, Wo = -(-H // stride), -(-W // stride)
+    out = torch.empty((N, T, Ho, Wo, C), dtype=x.dtype, device=x.device)
+    partial = None
+    if want_se:
+        nblk = expand_dw2_supported(T, H, W, cin, C, stride)
+        if nblk <= 0:
+            raise _lib.X3DLibError("x3d_expand_dw2_partial_blocks rejected the shape")
+        partial = torch.empty((N, nblk, C), dtype=torch.float32, device=x.device)
+    npad, kpad = wa.shape
+    _launch("x3d_expand_dw2_fwd", lambda: lib().x3d_expand_dw2_fwd(
+        x.data_ptr(), wa.data_ptr(), bias_a.data_ptr(), wb.data_ptr(), bias_b.data_ptr(),
+        out.data_ptr(), _ptr(partial), N, T, H, W, cin, C, kpad, npad, stride, pad_h, pad_w,
+        1 if swish else 0, _stream()))
+    return out, partial
+
+
 def se_mlp_fwd(partial: torch.Tensor, count: int, w1: torch.Tensor, b1: torch.Tensor,
                w2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
     N, nblk, C = partial.shape
