@@ -24,7 +24,8 @@ def _model(variant, dtype=None, views=None, seed=1111, graph=False):
         cfg.TEST.NUM_TEMPORAL_VIEWS, cfg.TEST.NUM_SPATIAL_CROPS = views, 1
     cfg.freeze()
     m = M.X3D(cfg, dtype=dtype, use_cuda_graph=graph)
-    W = synthetic_weights(build_arch(cfg), seed=seed)
+    # heavy-tailed class scales: the top-1 of (almost) every clip is decided at the error level
+    W = synthetic_weights(build_arch(cfg), seed=seed, head_spread=1.5)
     m.set_weights_dict(W)
     return m, cfg, W, O.OracleSpec.from_cfg(cfg)
 
@@ -37,6 +38,7 @@ def _check_logits(got, want, tol, check_top1):
         srt = np.sort(want, -1)
         margin = srt[:, -1] - srt[:, -2]
         decided = margin > 2 * np.abs(got - want).max()
+        assert decided.mean() >= 0.5, "fixture too flat: top-1 undecided on most clips"
         assert (got.argmax(-1)[decided] == want.argmax(-1)[decided]).all()
     return err
 
@@ -189,8 +191,8 @@ def test_predict_pipelined_host_batches_equal_call():
                                                      ("X3D_S", 13, 182, 3, 6),        # configs[1] shape, 3-crop
                                                      ("X3D_L", 16, 356, 1, 3)])       # configs[3] shape
 def test_full_size_properties(variant, T, S, views, clips):
-    """At BASELINE.json's full clip sizes (where the fp64 oracle is only affordable for one clip):
-    one clip against the oracle, then size-independent properties for the whole batch -- a clip's
+    """At BASELINE.json's full clip sizes (where the fp64 oracle is only affordable for a couple of
+    clips): two clips against the oracle, then size-independent properties for the whole batch -- a clip's
     logits do not depend on the batch it is in, the video probabilities are the mean of its views'
     softmaxes, rows sum to one, and the graph replay reproduces the eager launches bit for bit."""
     m, cfg, W, spec = _model(variant, dtype="bfloat16", views=views)
@@ -199,12 +201,13 @@ def test_full_size_properties(variant, T, S, views, clips):
     probs = m(xd).clone()
     logits = m.last_logits.clone()
     assert torch.isfinite(logits).all() and probs.shape == (clips // views, cfg.NETWORK.NUM_CLASSES)
-    # (1) one full-size clip against the float64 oracle
+    # (1) full-size clips against the float64 oracle: the first and the last of the batch (two
+    # different videos; one for X3D-L, whose fp64 forward is the slowest), with identical top-1
     spec1 = O.OracleSpec.from_cfg(cfg)
     spec1.num_preds = 1
-    want = O.forward(W, spec1, x[:1], torch.float64)["logits"]
-    err = rel_err(to_np(logits[:1]), want)
-    assert err < BF16_TOL, err
+    pick = [0] if variant == "X3D_L" else [0, clips - 1]
+    want = O.forward(W, spec1, x[pick], torch.float64)["logits"]
+    _check_logits(to_np(logits[pick]), want, BF16_TOL, True)
     # (2) batch independence: the last `views` clips alone
     m(xd[-views:].contiguous())
     assert torch.equal(m.last_logits, logits[-views:])

@@ -272,10 +272,16 @@ class PointwiseConv:
 class Options:
     pointwise = "tc"          # "tc": tcgen05 kernel for bf16 activations; "simt": CUDA-core GEMM
     stem = "tc"               # "tc": tcgen05 implicit-GEMM stem for bf16 activations; "simt"
-    # bf16 + "tc": run a/bn_a/relu/b/bn_b as ONE kernel (x3d_expand_dw_fwd).  Parity-green, but on
-    # B200 it is only break-even with the two-kernel path today (profiles/r01_fused_expand_dw.md),
-    # so it is opt-in.
-    fuse_expand = False
+    # bf16 + "tc": run a/bn_a/relu/b/bn_b (+ swish) as ONE kernel, the persistent warp-specialised
+    # x3d_expand_dw2_fwd (csrc/x3d_ab_persist.cu).  Parity-green on every layer shape, but NOT faster
+    # than the two-kernel path on B200: at 80 clips of 16x256^2 the three stage-2 blocks take 2.56 ms
+    # fused against 2.46 ms for the pair (with pixel pairing and the swish epilogue), all 26 blocks
+    # 8.37 against 7.61 ms; step 10.95 ms off / 11.09 ms stage 2 only / 11.88 ms everywhere.  The
+    # stencil half is bound by register-file bandwidth of the packed FFMA2 stream, not by the HBM
+    # traffic fusion removes (profiles/r02_fused_expand_dw.md), so it stays opt-in:
+    #   "off" (default); "auto": layers whose inner width fits one channel chunk (<= 72: stage 2);
+    #   "all": every layer with a tile plan; "v1": the round-1 one-CTA-per-tile kernel.
+    fuse_expand = os.environ.get("X3D_FUSE_EXPAND", "off")
     # uint8 clips in bf16 mode: "normalize" = x3d_normalize_u8 then the ordinary stem;
     # "fused" = x3d_stem_tc_u8_fwd (the stem's loader reads bytes through a lookup table)
     stem_u8 = "normalize"
@@ -452,7 +458,15 @@ class Bottleneck(Layer):
         tc = _use_tc()
         _, ph, _ = A.same_pad(H, 3, self.stride)
         _, pw, _ = A.same_pad(W, 3, self.stride)
-        if tc and Options.fuse_expand and x.dtype == torch.bfloat16 and \
+        mode = Options.fuse_expand
+        fuse2 = tc and x.dtype == torch.bfloat16 and (mode == "all" or (mode == "auto" and ci <= 72)) and \
+            ops.expand_dw2_supported(T, H, W, x.shape[-1], ci, self.stride) > 0
+        if fuse2:
+            ops.Profiler.tag = "ab"
+            swish_in_b = Options.swish_in_dw and not self.has_se
+            b, partial = ops.expand_dw2_fwd(x, d["a"].wp, d["a"].bias, d["wb"], d["bb"],
+                                            self.stride, ph, pw, self.has_se, swish=swish_in_b)
+        elif tc and mode == "v1" and x.dtype == torch.bfloat16 and \
                 ops.expand_dw_supported(T, H, W, x.shape[-1], ci, self.stride) > 0:
             ops.Profiler.tag = "ab"
             b, partial = ops.expand_dw_fwd(x, d["a"].wp, d["a"].bias, d["wb"], d["bb"],
@@ -741,7 +755,8 @@ class X3D(Layer):
         first use (after one eager run that warms lazy CUDA state).  Slots > 0 are extra captures
         over their own input/output buffers that share slot 0's memory pool (replays are
         stream-ordered), used by `predict` to overlap the H2D copy of the next batch."""
-        key = (tuple(shape), dtype, str(device), Options.pointwise, Options.stem, Options.stem_u8, Options.swish_in_dw, slot)
+        key = (tuple(shape), dtype, str(device), Options.pointwise, Options.stem, Options.stem_u8, Options.swish_in_dw,
+               Options.fuse_expand, slot)
         if key not in self._graphs:
             static_in = torch.zeros(tuple(shape), dtype=dtype, device=device)
             self._forward(static_in, training)

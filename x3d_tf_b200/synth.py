@@ -14,9 +14,15 @@ import numpy as np
 from .arch import ArchSpec, variable_shapes
 
 
-def synthetic_weights(arch: ArchSpec, seed: int = 1111) -> Dict[str, np.ndarray]:
+def synthetic_weights(arch: ArchSpec, seed: int = 1111, head_spread: float = 0.0) -> Dict[str, np.ndarray]:
     """Glorot-uniform kernels (Keras default initialiser), BN gamma~U[0.5,1.5],
-    beta~N(0,0.1), moving_mean~N(0,0.1), moving_variance~U[0.5,1.5], small biases."""
+    beta~N(0,0.1), moving_mean~N(0,0.1), moving_variance~U[0.5,1.5], small biases.
+
+    `head_spread` > 0 (parity fixtures): the columns of `fc2/kernel` and the entries of `fc2/bias`
+    are scaled by exp(N(0, head_spread)) per class.  With 400 near-Gaussian logits the top-1 /
+    top-2 gap of a random-weight network is a few percent of the largest logit; a log-normal
+    spread of the class scales makes the ranking heavy-tailed, so "identical top-1" becomes a
+    decided question at the bf16 tolerance on every fixture clip."""
     rng = np.random.default_rng(seed)
     out: Dict[str, np.ndarray] = {}
     for name, shp in variable_shapes(arch).items():
@@ -43,6 +49,10 @@ def synthetic_weights(arch: ArchSpec, seed: int = 1111) -> Dict[str, np.ndarray]
         else:
             raise KeyError(name)
         out[name] = a.astype(np.float32)
+    if head_spread > 0.0:
+        g = np.exp(np.random.default_rng(seed + 7919).normal(0.0, head_spread, size=out["fc2/bias"].shape))
+        out["fc2/kernel"] = (out["fc2/kernel"] * g[None, :]).astype(np.float32)
+        out["fc2/bias"] = (out["fc2/bias"] * g).astype(np.float32)
     return out
 
 
