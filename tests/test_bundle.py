@@ -71,7 +71,7 @@ def test_write_read_round_trip(tmp_path):
     tb.write_bundle(prefix, tensors, block_size=512)      # small blocks: many data blocks
     assert tb.latest_checkpoint(str(tmp_path / "ckpt")) == prefix
     rd = tb.BundleReader(prefix)
-    assert rd.keys() == sorted(k + tb.VAR_SUFFIX for k in tensors)
+    assert rd.keys() == sorted([k + tb.VAR_SUFFIX for k in tensors] + [tb.OBJECT_GRAPH_KEY])
     for k, v in tensors.items():
         got = rd.tensor(k + tb.VAR_SUFFIX)
         assert got.dtype == v.dtype and got.shape == v.shape and np.array_equal(got, v)
@@ -184,3 +184,61 @@ def test_from_scratch_init_is_keras_default():
     assert b.shape == (3, 3, 3, 1, 54) and np.abs(b).max() <= np.sqrt(6.0 / (27 + 27 * 54)) + 1e-7
     W2 = keras_default_weights(get_config("X3D_M"), seed=1111)
     assert all(np.array_equal(W[k], W2[k]) for k in W)
+
+
+def test_written_checkpoint_carries_a_keras_object_graph(tmp_path, checkpoint_index, B=tb):
+    """`write_bundle` emits `_CHECKPOINTABLE_OBJECT_GRAPH` (utils.py:128-132 checkpoints, read back by
+    train.py:137 / eval.py:81 through Keras' object-based restore): a DT_STRING scalar in TF's string
+    framing whose TrackableObjectGraph reaches EVERY variable of the shipped X3D-M index by walking
+    `local_name` edges along its checkpoint key, with the momentum slots hung off the optimizer node."""
+    from x3d_tf_b200.arch import build_arch
+    from x3d_tf_b200.config import get_config
+    from x3d_tf_b200.synth import synthetic_weights
+    W = synthetic_weights(build_arch(get_config("X3D_M")), seed=1)
+    slots = {k: np.zeros_like(v) for k, v in W.items()
+             if not k.endswith(("moving_mean", "moving_variance"))}
+    tensors = dict(W)
+    tensors.update(B.optimizer_tensors(1876480, 0.05, 0.9, slots))
+    prefix = str(tmp_path / "ckpt-3")
+    B.write_bundle(prefix, tensors)
+    rd = B.BundleReader(prefix)
+    suffix = "/.ATTRIBUTES/VARIABLE_VALUE"
+    shipped = {e[0] for e in checkpoint_index["keys"]}
+    assert set(rd.keys()) == shipped                          # incl. the object graph and the "" header
+    e = rd.entries[B.OBJECT_GRAPH_KEY]
+    assert e.dtype == B.DT_STRING and e.shape == ()
+    (proto,) = rd.string_tensor(B.OBJECT_GRAPH_KEY)
+    assert e.size == len(proto) + 4 + len(B._put_varint(len(proto)))          # TF's string-tensor framing
+    raw = bytes(rd._shard(0)[e.offset:e.offset + e.size])
+    assert B.unmask_crc(e.crc32c) == B.crc32c(proto, B.crc32c(raw[len(raw) - len(proto) - 4:len(raw) - len(proto)],
+                                                               B.crc32c(np.uint32(len(proto)).tobytes())))
+    nodes = B.parse_object_graph(proto)
+    var_keys = sorted(k for k in shipped if k.endswith(suffix))
+    assert len(var_keys) == 788
+    reached = set()
+    opt = nodes[0]["children"]["optimizer"]
+    slot_of = {(v, name): sid for v, name, sid in nodes[opt]["slot_variables"]}
+    assert len(slot_of) == 308
+    for k in var_keys:
+        path = k[:-len(suffix)]
+        if "/.OPTIMIZER_SLOT/" in path:
+            var_path, rest = path.split("/.OPTIMIZER_SLOT/")
+            assert rest == "optimizer/momentum"
+            cur = 0
+            for part in var_path.split("/"):
+                cur = nodes[cur]["children"][part]
+            nid = slot_of[(cur, "momentum")]
+        else:
+            nid = 0
+            for part in path.split("/"):
+                nid = nodes[nid]["children"][part]            # KeyError = Keras could not match the dependency
+        (name, full, key), = nodes[nid]["attributes"]
+        assert name == "VARIABLE_VALUE" and key == k
+        reached.add(nid)
+    assert len(reached) == 788
+    # interior nodes carry no tensors; the root is node 0 and has the model's attribute names
+    assert {"conv1", "stages", "conv5", "fc1", "fc2", "optimizer"} <= set(nodes[0]["children"])
+    assert set(nodes[nodes[0]["children"]["stages"]]["children"]) == {"0", "1", "2", "3"}
+    # model variables still load by name, the graph entry is ignored there
+    got = B.load_model_variables(prefix)
+    assert sorted(got) == sorted(W)

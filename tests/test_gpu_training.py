@@ -42,8 +42,9 @@ def _l2(got, want):
     return float(np.linalg.norm(np.asarray(got, np.float64) - want) / max(np.linalg.norm(want), 1e-30))
 
 
-@pytest.mark.parametrize("variant,n,s", [("X3D_XS", 2, 64), ("X3D_S", 2, 91)])
-def test_training_step_matches_autograd_oracle(variant, n, s):
+@pytest.mark.parametrize("variant,n,t,s", [("X3D_XS", 2, 4, 64), ("X3D_S", 2, 4, 91),
+                                           ("X3D_M", 2, 16, 224)])        # BASELINE configs[4] clip shape
+def test_training_step_matches_autograd_oracle(variant, n, t, s):
     """loss, every gradient, the SGD-Nesterov update and the moving statistics of ONE step against
     float64 autograd.
 
@@ -54,7 +55,7 @@ def test_training_step_matches_autograd_oracle(variant, n, s):
     that, every gradient must agree to 1e-3 of its tensor's largest value.  A second pass without
     the masks bounds the effect of the flips (0.25 in the L2 norm; ~7e-2 worst case measured at this
     tiny batch, where one flip is 1/32 of a channel's statistics)."""
-    cfg, W, x, labels, mask, tr = _setup(variant, n=n, s=s)
+    cfg, W, x, labels, mask, tr = _setup(variant, n=n, t=t, s=s)
     tr.relu_masks = []
     lr, wd = 0.05, float(cfg.NETWORK.WEIGHT_DECAY)
     loss = tr.step(torch.from_numpy(x).cuda(), torch.from_numpy(labels).cuda(), lr)
@@ -232,3 +233,53 @@ def test_adam_step_matches_oracle(tmp_path):
     st = tr2.load_checkpoint(prefix, strict_slots=True)
     assert st["iter"] == 2 and abs(st["beta_2"] - 0.999) < 1e-6
     assert torch.equal(tr2.v, tr.v) and torch.equal(tr2.v2, tr.v2) and torch.equal(tr2.w, tr.w)
+
+
+def test_class_api_training_mode_and_fit():
+    """`X3D.call(x, training=True)` (model.py:113-127 in training mode: batch-statistics BN, moving
+    statistics updated, per-clip softmax) and `X3D.fit` (train.py:145-152) run the training kernels
+    behind the Keras-named class: logits / moving statistics against the float64 oracle, and `fit`
+    leaves exactly the variables a stand-alone X3DTrainer produces from the same batches."""
+    from x3d_tf_b200 import model as M
+    from x3d_tf_b200.arch import build_arch
+    from x3d_tf_b200.config import get_config
+    from x3d_tf_b200.synth import synthetic_clips, synthetic_weights
+    from x3d_tf_b200.training import X3DTrainer
+    cfg = get_config("X3D_XS", freeze=False)
+    cfg.NETWORK.DROPOUT_RATE = 0.0
+    cfg.freeze()
+    W = synthetic_weights(build_arch(cfg), seed=5)
+    x = synthetic_clips(2, 4, 64, 64, cfg.DATA.MEAN, cfg.DATA.STD, seed=6)
+    labels = np.array([7, 311], np.int32)
+    M.reset_block_counters()
+    m = M.X3D(cfg)
+    m.set_weights_dict(W)
+    probs = m(torch.from_numpy(x).cuda(), training=True)
+    torch.cuda.synchronize()
+    ref = TO.train_step(W, O.OracleSpec.from_cfg(cfg), x, labels, lr=0.0, momentum=0.9, weight_decay=0.0,
+                        dropout_mask=None)
+    assert probs.shape == (2, 400)
+    assert _rel(m.last_logits.cpu().numpy(), ref["logits"]) < 1e-4
+    np.testing.assert_allclose(probs.cpu().numpy().sum(-1), 1.0, rtol=1e-5)
+    got = m.named_variables()
+    for k in ("conv1/bn/moving_mean", "conv1/bn/moving_variance", "conv5/layer_with_weights-1/moving_mean"):
+        assert _rel(got[k], ref["weights"][k]) < 1e-4, k                     # Keras updates them in training mode
+    assert np.array_equal(got["fc2/kernel"], W["fc2/kernel"])                # ... and nothing else
+    with pytest.raises(NotImplementedError):
+        m.stages[0](torch.zeros(1, 2, 8, 8, 24).cuda(), training=True)       # blocks: see INTEGRATION.md
+    # fit == the stand-alone trainer on the same batches
+    M.reset_block_counters()
+    m2 = M.X3D(cfg)
+    m2.set_weights_dict(W)
+    data = [(x, labels), (x[::-1].copy(), labels[::-1].copy())]
+    hist = m2.fit(data, epochs=1, lr_schedule=lambda e: 0.01)
+    assert len(hist["loss"]) == 1 and np.isfinite(hist["loss"][0])
+    tr = X3DTrainer(cfg).load(W)
+    for c, l in data:
+        tr.step(torch.from_numpy(c).cuda(), torch.from_numpy(l).cuda(), 0.01)
+    torch.cuda.synchronize()
+    Wt, Wm = tr.weights(), m2.named_variables()
+    assert all(np.array_equal(Wt[k], Wm[k]) for k in Wt)
+    assert not np.array_equal(Wm["fc2/kernel"], W["fc2/kernel"])
+    p2 = m2(torch.from_numpy(x).cuda())                                      # inference sees the trained values
+    assert p2.shape == (2, 400) and torch.isfinite(p2).all()

@@ -140,8 +140,9 @@ class Layer:
     def _no_training(training: bool):
         if training:
             raise NotImplementedError(
-                "training=True (batch-statistics BatchNorm, dropout) is not built yet; only the "
-                "inference path of model.py:113-127 is implemented (see DESIGN.md, scope)")
+                "training=True on a stand-alone block: the training kernels (batch-statistics BatchNorm, "
+                "dropout, backward) run on the whole model's flat parameter arena -- use "
+                "X3D.call(x, training=True) / X3D.fit(...) (training.X3DTrainer), see INTEGRATION.md")
 
     def _fold_bn(self, key: str, eps: float) -> Tuple[np.ndarray, np.ndarray]:
         g = self._vars[f"{key}/gamma"].astype(np.float64)
@@ -707,10 +708,6 @@ class X3D(Layer):
         self.fc2 = self._child("fc2", _Dense("fc_2", (2048, self.num_classes), bias=True))
 
     # ---- weights
-    def set_weights_dict(self, weights, prefix: str = "", strict: bool = True):
-        self._graphs.clear()
-        return super().set_weights_dict(weights, prefix, strict)
-
     def load_weights(self, filepath: str, verify: bool = True) -> _LoadStatus:
         """Restore from a TF-format checkpoint prefix (`train.py:137-143`, `eval.py:78-81`)."""
         names = set(self.named_variables())
@@ -773,10 +770,91 @@ class X3D(Layer):
     def __call__(self, x, training: bool = False, copy: bool = True):
         return self.call(x, training=training, copy=copy)
 
+    # ---- training mode behind the class API (train.py:128-152)
+    def _trainer(self):
+        """The training engine for this model's variables (training.X3DTrainer: batch-statistics BN,
+        dropout, backward kernels, gradient exchange, optimizer), created on first use from the
+        current variables; `_sync_from_trainer` copies trained values back into them."""
+        if getattr(self, "_tr", None) is None:
+            import torch.distributed as dist
+            from .training import X3DTrainer
+            world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+            rank = dist.get_rank() if world > 1 else 0
+            dev = self._device or torch.device("cuda", torch.cuda.current_device())
+            self._tr = X3DTrainer(self.cfg, device=dev, world=world, rank=rank).load(dict(self.named_variables()))
+        return self._tr
+
+    def _sync_from_trainer(self):
+        if getattr(self, "_tr", None) is not None:
+            self.set_weights_dict(self._tr.weights(), strict=False)
+
+    def set_weights_dict(self, weights, prefix: str = "", strict: bool = True):
+        self._graphs.clear()
+        missing = super().set_weights_dict(weights, prefix, strict)
+        if getattr(self, "_tr", None) is not None and not getattr(self, "_syncing", False):
+            self._tr = None                              # rebuilt from the new values on next use
+        return missing
+
+    def fit(self, dataset, epochs: int = 1, initial_epoch: int = 0, steps_per_epoch: Optional[int] = None,
+            lr_schedule=None, verbose: int = 0, **_):
+        """Keras `model.fit` as train.py:145-152 uses it: for every epoch the learning rate comes from
+        `lr_schedule(epoch)` (train.py:114-125, default training.lr_schedule of this model's cfg),
+        `steps_per_epoch` batches `(clips, labels)` are taken from `dataset` (re-iterated per epoch),
+        each one forward + backward + gradient all-reduce over the initialised torch.distributed
+        group + optimizer step (cfg.TRAIN.OPTIMIZER).  Returns {"loss": [per-epoch mean]}.  The model's
+        variables hold the trained values afterwards (call / evaluate / save_weights see them)."""
+        from . import ops
+        from .training import lr_schedule as default_schedule
+        tr = self._trainer()
+        sched = lr_schedule or (lambda e: default_schedule(self.cfg, e))
+        dev = tr.device
+        mean, std = tuple(self.cfg.DATA.MEAN), tuple(self.cfg.DATA.STD)
+        hist = {"loss": [], "lr": []}
+        for epoch in range(initial_epoch, epochs):
+            lr = float(sched(epoch))
+            tot, n = torch.zeros((), dtype=torch.float64, device=dev), 0
+            for i, (clips, labels) in enumerate(dataset):
+                if steps_per_epoch is not None and i >= steps_per_epoch:
+                    break
+                x = _as_device_clip(clips, dev)
+                if x.dtype == torch.uint8:
+                    x = ops.normalize_u8(x, mean, std, torch.float32)
+                lab = torch.as_tensor(np.asarray(labels.cpu() if isinstance(labels, torch.Tensor) else labels)
+                                      .reshape(-1), dtype=torch.int32).to(dev)
+                loss = tr.step(x.float(), lab, lr)
+                tot += loss.double().mean()
+                n += 1
+            hist["loss"].append(float(tot / max(n, 1)))
+            hist["lr"].append(lr)
+            if verbose:
+                print(f"Epoch {epoch + 1}/{epochs} - loss: {hist['loss'][-1]:.4f} - lr: {lr:.5f}")
+        self._syncing = True
+        try:
+            self._sync_from_trainer()
+        finally:
+            self._syncing = False
+        return hist
+
     def call(self, input, training: bool = False, copy: bool = True):
         """`copy=False` returns the CUDA graph's static output buffers (valid until the next call
-        with the same input shape) instead of fresh tensors: the zero-allocation path bench.py times."""
-        self._no_training(training)
+        with the same input shape) instead of fresh tensors: the zero-allocation path bench.py times.
+        `training=True`: batch-statistics BatchNorm + dropout through the training kernels (fp32;
+        moving statistics are updated as Keras does), per-clip softmax without view averaging
+        (model.py:122-127)."""
+        if training:
+            x = _as_device_clip(input, self._device)
+            if x.dtype == torch.uint8:
+                x = ops.normalize_u8(x, tuple(self.cfg.DATA.MEAN), tuple(self.cfg.DATA.STD), torch.float32)
+            tr = self._trainer()
+            logits = tr.forward_training(x.float())
+            tr.iteration += 1                            # a fresh dropout mask per training-mode call
+            self.last_logits = logits
+            self._syncing = True
+            try:
+                self._sync_from_trainer()                # the moving statistics moved
+            finally:
+                self._syncing = False
+            return ops.softmax_viewmean_fwd(logits.contiguous(), 1)
         x = _as_device_clip(input, self._device)
         self._check_input(x.shape)
         if not self._use_graph:

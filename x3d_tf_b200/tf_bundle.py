@@ -296,6 +296,16 @@ class BundleReader:
             self._shards[shard_id] = np.memmap(path, dtype=np.uint8, mode="r")
         return self._shards[shard_id]
 
+    def string_tensor(self, key: str) -> List[bytes]:
+        """A DT_STRING entry (e.g. `_CHECKPOINTABLE_OBJECT_GRAPH`) as a list of byte strings."""
+        e = self.entries[key]
+        if e.dtype != DT_STRING:
+            raise BundleError(f"{key}: not a string tensor")
+        shard = self._shard(e.shard_id)
+        raw = bytes(shard[e.offset:e.offset + e.size])
+        n = int(np.prod(e.shape, dtype=np.int64)) if e.shape else 1
+        return _parse_string_tensor(raw, n)
+
     def tensor(self, key: str, verify: bool = True) -> np.ndarray:
         e = self.entries[key]
         if e.has_slices:
@@ -410,6 +420,134 @@ def optimizer_tensors(iteration: int, learning_rate: float, momentum: float, slo
     return out
 
 
+# ------------------------------------------------------------------------------ Keras object graph
+OBJECT_GRAPH_KEY = "_CHECKPOINTABLE_OBJECT_GRAPH"
+_SLOT_MARK = "/.OPTIMIZER_SLOT/"
+
+
+def _pb_str(field: int, b: bytes) -> bytes:
+    return _put_varint(field << 3 | 2) + _put_varint(len(b)) + b
+
+
+def _pb_int(field: int, v: int) -> bytes:
+    return _put_varint(field << 3 | 0) + _put_varint(v)
+
+
+def object_graph_proto(checkpoint_keys: Iterable[str]) -> bytes:
+    """Serialized `TrackableObjectGraph` (tensorflow/core/protobuf/trackable_object_graph.proto) for
+    the variables named by `checkpoint_keys` (full keys, ending in /.ATTRIBUTES/VARIABLE_VALUE).
+
+    Keras' object-based `load_weights` (train.py:137, eval.py:81) does not look tensors up by name: it
+    walks this graph from node 0 (the model), matching each object's dependencies by `local_name`
+    (`conv1`, `stages` -> `0` -> `stage` -> `layer_with_weights-0` -> `bottleneck` -> `a` -> `kernel`,
+    ...), and reads a matched variable from the `checkpoint_key` of its VARIABLE_VALUE attribute.  The
+    checkpoint keys ARE those dependency paths, so the graph is the trie of the keys; slot variables
+    (`<variable path>/.OPTIMIZER_SLOT/optimizer/<slot>`) hang off the `optimizer` node as
+    `slot_variables {original_variable_node_id, slot_name, slot_variable_node_id}`.  Aliases Keras also
+    records (`layer-N`, `layer_with_weights-N` on the model, `keras_api`) are optional for restore and
+    are not emitted."""
+    children: List[Dict[str, int]] = [{}]             # node id -> {local_name: child id}
+    attr: Dict[int, Tuple[str, str]] = {}             # variable node id -> (full_name, checkpoint_key)
+    slots: List[Tuple[str, str, str]] = []            # (variable path, optimizer path, slot name)
+
+    def node_for(path: str) -> int:
+        cur = 0
+        for part in path.split("/"):
+            nxt = children[cur].get(part)
+            if nxt is None:
+                nxt = len(children)
+                children.append({})
+                children[cur][part] = nxt
+            cur = nxt
+        return cur
+
+    keys = sorted(k for k in checkpoint_keys if k.endswith(VAR_SUFFIX))
+    for k in keys:
+        path = k[:-len(VAR_SUFFIX)]
+        if _SLOT_MARK in path:
+            var_path, rest = path.split(_SLOT_MARK, 1)
+            opt_path, slot_name = rest.rsplit("/", 1)
+            slots.append((var_path, opt_path, slot_name))
+        else:
+            attr[node_for(path)] = (path, k)
+    slot_refs: Dict[int, List[Tuple[int, str, int]]] = {}
+    for var_path, opt_path, slot_name in slots:
+        var_id, opt_id = node_for(var_path), node_for(opt_path)
+        sid = len(children)
+        children.append({})
+        key = f"{var_path}{_SLOT_MARK}{opt_path}/{slot_name}{VAR_SUFFIX}"
+        attr[sid] = (f"{var_path}/{slot_name}", key)
+        slot_refs.setdefault(opt_id, []).append((var_id, slot_name, sid))
+    out = bytearray()
+    for nid, ch in enumerate(children):
+        body = bytearray()
+        for name, cid in ch.items():
+            body += _pb_str(1, _pb_int(1, cid) + _pb_str(2, name.encode("utf-8")))
+        if nid in attr:
+            full, key = attr[nid]
+            body += _pb_str(2, _pb_str(1, b"VARIABLE_VALUE") + _pb_str(2, full.encode("utf-8")) +
+                            _pb_str(3, key.encode("utf-8")))
+        for var_id, slot_name, sid in slot_refs.get(nid, []):
+            body += _pb_str(3, _pb_int(1, var_id) + _pb_str(2, slot_name.encode("utf-8")) + _pb_int(3, sid))
+        out += _pb_str(1, bytes(body))
+    return bytes(out)
+
+
+def parse_object_graph(proto: bytes) -> List[dict]:
+    """Inverse of `object_graph_proto` (tests; also reads the graph of a real Keras checkpoint):
+    [{"children": {local_name: id}, "attributes": [(name, full_name, checkpoint_key)],
+      "slot_variables": [(original_variable_node_id, slot_name, slot_variable_node_id)]}, ...]."""
+    nodes = []
+    for f, _, node in _pb_fields(proto):
+        if f != 1:
+            continue
+        d = {"children": {}, "attributes": [], "slot_variables": []}
+        for g, _, v in _pb_fields(node):
+            sub = {h: w for h, _, w in _pb_fields(v)}
+            if g == 1:
+                d["children"][bytes(sub.get(2, b"")).decode("utf-8")] = int(sub.get(1, 0))
+            elif g == 2:
+                d["attributes"].append(tuple(bytes(sub.get(i, b"")).decode("utf-8") for i in (1, 2, 3)))
+            elif g == 3:
+                d["slot_variables"].append((int(sub.get(1, 0)), bytes(sub.get(2, b"")).decode("utf-8"),
+                                            int(sub.get(3, 0))))
+        nodes.append(d)
+    return nodes
+
+
+def _string_tensor(strings: List[bytes]) -> Tuple[bytes, int]:
+    """On-disk form of a DT_STRING tensor (tensor_bundle.cc WriteStringTensor): [varint64 length]*,
+    masked CRC-32C of the lengths (each as a little-endian uint32), the bytes.  Returns (raw, crc):
+    crc covers the lengths, the length checksum and the bytes."""
+    raw, crc = bytearray(), 0
+    for b in strings:
+        raw += _put_varint(len(b))
+        crc = crc32c(struct.pack("<I", len(b)), crc)
+    cks = struct.pack("<I", mask_crc(crc))
+    raw += cks
+    crc = crc32c(cks, crc)
+    for b in strings:
+        raw += b
+        crc = crc32c(b, crc)
+    return bytes(raw), crc
+
+
+def _parse_string_tensor(raw: bytes, n: int) -> List[bytes]:
+    pos, lens, crc = 0, [], 0
+    for _ in range(n):
+        v, pos = _get_varint(raw, pos)
+        lens.append(v)
+        crc = crc32c(struct.pack("<I", v), crc)
+    if struct.unpack("<I", raw[pos:pos + 4])[0] != mask_crc(crc):
+        raise BundleError("string tensor: length checksum mismatch")
+    pos += 4
+    out = []
+    for v in lens:
+        out.append(bytes(raw[pos:pos + v]))
+        pos += v
+    return out
+
+
 # ------------------------------------------------------------------------------ writer
 class _BlockBuilder:
     def __init__(self, restart_interval: int = 16):
@@ -447,18 +585,29 @@ def _emit_block(f, contents: bytes) -> Tuple[int, int]:
 
 
 def write_bundle(prefix: str, tensors: Dict[str, np.ndarray], block_size: int = 256 << 10,
-                 add_suffix: bool = True, state_file: bool = True) -> None:
+                 add_suffix: bool = True, state_file: bool = True, object_graph: bool = True) -> None:
     """Write `{prefix}.index` + `{prefix}.data-00000-of-00001` holding `tensors`
-    (float32 / int64 / ...), keys sorted like TF's writer does.  Not a full Keras checkpoint:
-    no object graph is emitted, so it is readable by name (this reader,
-    `tf.train.load_checkpoint`) but not by Keras' object-based `load_weights`."""
+    (float32 / int64 / ...), keys sorted like TF's writer does, plus (by default) the
+    `_CHECKPOINTABLE_OBJECT_GRAPH` string tensor Keras' object-based `load_weights` walks
+    (`object_graph_proto`), so that the reference's `train.py:137` / `eval.py:81` can restore what
+    `X3D.save_weights` / `X3DTrainer.save_checkpoint` write."""
     items = sorted(((k + VAR_SUFFIX if add_suffix else k), v) for k, v in tensors.items())
+    if object_graph and add_suffix:
+        items.append((OBJECT_GRAPH_KEY, object_graph_proto(k for k, _ in items)))
+        items.sort(key=lambda kv: kv[0])
     os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
     entries: List[Tuple[bytes, bytes]] = []
     header = b"\x08\x01" + b"\x1a\x02\x08\x01"        # num_shards=1, version{producer=1}
     entries.append((b"", header))
     with open(prefix + ".data-00000-of-00001", "wb") as df:
         for k, arr in items:
+            if isinstance(arr, (bytes, bytearray)):                  # scalar DT_STRING tensor
+                raw, c = _string_tensor([bytes(arr)])
+                e = BundleEntry(dtype=DT_STRING, shape=(), shard_id=0, offset=df.tell(), size=len(raw),
+                                crc32c=mask_crc(c))
+                df.write(raw)
+                entries.append((k.encode("utf-8"), e.serialize()))
+                continue
             a = np.asarray(arr, order="C")
             dt = a.dtype.newbyteorder("<") if a.dtype.byteorder == ">" else a.dtype
             if np.dtype(dt) not in _DT_OF_NP:

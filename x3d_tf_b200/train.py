@@ -179,9 +179,8 @@ def run(argv: Optional[List[str]] = None) -> Optional[dict]:
         stats = torch.stack([loss_sum, torch.tensor(float(n * batch), dtype=torch.float64, device=dev)])
         if world > 1:
             dist.all_reduce(stats)
-            for t in tr.moving.values():                                     # average at save time
-                dist.all_reduce(t)
-                t /= world
+            from .exchange import average_
+            average_(tr.moving.values(), world)                              # average at save time
         log = {"epoch": epoch + 1, "lr": lr, "loss": float(stats[0] / max(float(stats[1]), 1.0)),
                "steps": n, "seconds": time.time() - t0}
         if val_items is not None:

@@ -134,6 +134,22 @@ class X3DTrainer:
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)          # SGD momentum / Adam m
         self.v2 = torch.zeros(n, dtype=torch.float32, device=dev) if self.optimizer == "adam" else None   # Adam v
         self.wd = torch.zeros(n, dtype=torch.float32, device=dev)
+        # gradient exchange (exchange.py): buckets cut where stages 4 and 5 (s = 2, 3) start, in backward
+        # order: [stage 5 + conv5 + fc1 + fc2] (83 % of the bytes), [stage 4] (15 %), [stem + stages 2, 3]
+        from .exchange import GradientExchange, make_buckets
+        edges, self._bucket_of_stage = [], {}
+        for st in (2, 3):
+            first = next((k for k in self.layout.slots if k.startswith(f"stages/{st}/")), None)
+            if first is not None:
+                edges.append(self.layout.slots[first][0])
+        buckets = make_buckets(n, edges)
+        for st in (2, 3):
+            first = next((k for k in self.layout.slots if k.startswith(f"stages/{st}/")), None)
+            if first is not None:
+                self._bucket_of_stage[st] = next(i for i, (lo, hi) in enumerate(buckets)
+                                                 if lo == self.layout.slots[first][0])
+        self.exchange = GradientExchange(self.g, buckets, world, process_group)
+        self._converted: list = []
         for name in self.layout.slots:
             if self.decay[name]:
                 self.layout.view(self.wd, name).fill_(self.wd2)
@@ -303,7 +319,13 @@ class X3DTrainer:
         return out
 
     # ------------------------------------------------------------------ the step
-    def forward_backward(self, clips: torch.Tensor, labels: torch.Tensor):
+    def forward_training(self, clips: torch.Tensor) -> torch.Tensor:
+        """`model(clips, training=True)` of the reference (model.py:113-127 in training mode): batch-
+        statistics BatchNorm (moving statistics are updated, as Keras does), dropout, no view
+        averaging.  Returns the fc2 logits [N, classes]; no gradients are computed."""
+        return self.forward_backward(clips, None, backward=False)
+
+    def forward_backward(self, clips: torch.Tensor, labels: Optional[torch.Tensor], backward: bool = True):
         """clips [N,T,H,W,3] fp32 on the device, labels [N] int32.  Leaves data-loss gradients
         (scaled by 1/world) in self.g64 and returns the per-clip losses."""
         ar, L = self.arch, lib()
@@ -311,6 +333,7 @@ class X3DTrainer:
         N, T, H, W, _ = x.shape
         self.g64.zero_()
         tape: List = []                       # backward closures, each maps dy -> dx of its op
+        self._exchange_started = False
 
         # ---- stem (model.py:202-208)
         cs = _pad8(ar.stem_channels)
@@ -337,6 +360,10 @@ class X3DTrainer:
 
         # ---- residual stages (model.py:384-394, 305-320)
         for b in ar.blocks:
+            if self.world > 1 and b.index == 0 and b.stage in self._bucket_of_stage:
+                # replayed AFTER every backward closure of this stage and of everything behind it: the
+                # gradients of the bucket that starts at this stage are complete -> start its all-reduce
+                tape.append(lambda d, k=self._bucket_of_stage[b.stage]: self._bucket_ready(k, d))
             act = self._block(act, b, tape)
 
         # ---- head (model.py:117-122)
@@ -380,6 +407,8 @@ class X3DTrainer:
             return self._pw_bwd(hd, dl, "fc2/kernel")
         tape.append(fc2_bwd)
         self.last_logits = logits
+        if not backward:
+            return logits
         loss = torch.empty(Nn, dtype=torch.float32, device=x.device)
         dlogits = torch.empty_like(logits)
         check(L.x3d_softmax_xent(logits.data_ptr(), labels.data_ptr(), loss.data_ptr(), dlogits.data_ptr(), Nn,
@@ -515,6 +544,15 @@ class X3DTrainer:
         tape.append(join_bwd)
         return out.view(N, T, Ho, Wo, co)
 
+    def _bucket_ready(self, k: int, d):
+        """Backward has finished bucket k of the gradient arena: fp64 accumulators -> fp32 arena for that
+        range, then its all-reduce starts while the backward pass continues (exchange.py)."""
+        lo, hi = self.exchange.buckets[k]
+        check(lib().x3d_d2f(self.g64[lo:hi].data_ptr(), self.g[lo:hi].data_ptr(), hi - lo, 1.0, _s()), "x3d_d2f")
+        self.exchange.start(k)
+        self._converted.append((lo, hi))
+        return d
+
     def _dropout_seed(self) -> int:
         """64-bit seed of this step's dropout stream: a hash of (seed, rank, iteration), so every
         data-parallel replica draws its own mask (per-replica RNG under MirroredStrategy) and the
@@ -523,12 +561,18 @@ class X3DTrainer:
 
     def step(self, clips: torch.Tensor, labels: torch.Tensor, lr: float) -> torch.Tensor:
         """forward + backward + gradient all-reduce + SGD-Nesterov update.  Returns per-clip losses."""
+        self._converted = []
         loss = self.forward_backward(clips, labels)
         n = self.layout.size
-        check(lib().x3d_d2f(self.g64.data_ptr(), self.g.data_ptr(), n, 1.0, _s()), "x3d_d2f")
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.g, op=dist.ReduceOp.SUM, group=self.pg)
+            # buckets whose all-reduce already runs behind the backward pass are done; the rest (the
+            # stem and the first stages, < 3 % of the bytes) is converted and exchanged now
+            for k, (lo, hi) in enumerate(self.exchange.buckets):
+                if (lo, hi) not in self._converted:
+                    self._bucket_ready(k, None)
+            self.exchange.finish()
+        else:
+            check(lib().x3d_d2f(self.g64.data_ptr(), self.g.data_ptr(), n, 1.0, _s()), "x3d_d2f")
         if self.optimizer == "adam":
             b1, b2, eps = self.adam
             t = self.iteration + 1
