@@ -247,6 +247,7 @@ def test_class_api_training_mode_and_fit():
     from x3d_tf_b200.training import X3DTrainer
     cfg = get_config("X3D_XS", freeze=False)
     cfg.NETWORK.DROPOUT_RATE = 0.0
+    cfg.TEST.NUM_TEMPORAL_VIEWS, cfg.TEST.NUM_SPATIAL_CROPS = 1, 1
     cfg.freeze()
     W = synthetic_weights(build_arch(cfg), seed=5)
     x = synthetic_clips(2, 4, 64, 64, cfg.DATA.MEAN, cfg.DATA.STD, seed=6)
