@@ -93,6 +93,20 @@ typedef struct x3d_pw_args {
 } x3d_pw_args;
 int x3d_pw_fwd(const x3d_pw_args* args, void* stream);
 
+/* fp32 pointwise conv on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMEM accumulator,
+ * TMA operands) with the 3xTF32 split -- fp32-level accuracy; the training path's GEMM (forward of
+ * a / c / shortcut / conv5 / fc1 / fc2, model.py:246-253, 292-299, 360-367, 78-108, and their
+ * backward-data):   D[M, Nc] = act(bias + A[M, K] . B^T)
+ *   A [M, lda] fp32, K % 4 == 0;  D [M, ldd] fp32, Nc % 4 == 0;  bias [Nc] fp32 or NULL;  relu 0/1
+ *   Bsplit fp32 [2][Nc][K]: plane 0 = B rounded to TF32, plane 1 = B - plane 0 (B = the [Nc, K]
+ *   operand with the reduction dimension contiguous), produced by
+ * x3d_tf32_split(W, out, rows, cols, ld, transpose): out[.][r][c] from W[r*ld + c], or from
+ *   W[c*ld + r] when transpose = 1 (forward: W is the [K, Nc] kernel, rows = Nc, cols = K, transpose;
+ *   backward-data: the same kernel as stored, rows = K, cols = Nc). */
+int x3d_tf32_split(const float* W, float* out, int rows, int cols, int ld, int transpose, void* stream);
+int x3d_pw_tf32_fwd(const float* A, const float* Bsplit, const float* bias, float* D, int64_t M, int K,
+                    int Nc, int lda, int ldd, int relu, void* stream);
+
 /* ---- Channelwise 3x3x3 convolution: Bottleneck.b + bn_b, model.py:309-310 -------------------
  * Grouped Conv3D(groups=C) stride (1,s,s), TF padding='same' (T: 1 before; H/W: pad_h/pad_w
  * before, derived on the host from TF's rule), + BN, and -- when `se_partial` != NULL -- the

@@ -205,3 +205,36 @@ def test_softmax_xent_and_sgd():
     v1 = 0.9 * v - 0.05 * gg
     _close(to_np(vd), v1, 1e-6)
     _close(to_np(wd_), w + 0.9 * v1 - 0.05 * gg, 1e-6)
+
+
+@pytest.mark.parametrize("M,K,N,relu,use_bias", [(1000, 24, 56, True, True), (4096, 56, 24, False, True),
+                                                 (300, 432, 192, False, False), (129, 192, 432, True, True),
+                                                 (64, 432, 2048, True, False), (32, 2048, 400, False, True),
+                                                 (5000, 48, 216, True, True), (12345, 216, 96, False, True)])
+def test_pointwise_tf32x3_tcgen05(M, K, N, relu, use_bias):
+    """x3d_pw_tf32_fwd (tcgen05.mma kind::tf32, 3xTF32 split) against float64: fp32-level accuracy
+    (2e-5 of the output's scale, the bound of the fp32 kernels) in both orientations -- forward
+    a . w and backward-data dy . w^T with the kernel read as stored."""
+    from x3d_tf_b200 import ops
+    rng = np.random.default_rng(M + K + N)
+    a = rng.normal(size=(M, K)).astype(np.float32)
+    w = (rng.normal(size=(K, N)) / np.sqrt(K)).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32) if use_bias else None
+    want = a.astype(np.float64) @ w.astype(np.float64) + (b if use_bias else 0.0)
+    if relu:
+        want = np.maximum(want, 0.0)
+    got = ops.pw_tf32(torch.from_numpy(a).cuda(), torch.from_numpy(w).cuda(),
+                      torch.from_numpy(b).cuda() if use_bias else None, relu=relu, transpose_w=True)
+    torch.cuda.synchronize()
+    scale = np.abs(want).max()
+    err = np.abs(got.cpu().numpy() - want).max() / scale
+    assert got.shape == (M, N) and err < 2e-5, err
+    # a single-pass TF32 product would be ~1e-3: make sure the split is really in effect (the tensor
+    # core's fp32 accumulation truncates, so the error grows with the reduction length)
+    assert err < (5e-6 if K <= 512 else 2e-5), err
+    dy = rng.normal(size=(M, N)).astype(np.float32)
+    want_dx = dy.astype(np.float64) @ w.astype(np.float64).T
+    dx = ops.pw_tf32(torch.from_numpy(dy).cuda(), torch.from_numpy(w).cuda(), None, transpose_w=False)
+    torch.cuda.synchronize()
+    assert dx.shape == (M, K)
+    assert np.abs(dx.cpu().numpy() - want_dx).max() / np.abs(want_dx).max() < (5e-6 if N <= 512 else 2e-5)

@@ -275,6 +275,31 @@ def expand_dw_fwd(x: torch.Tensor, wa: torch.Tensor, bias_a: torch.Tensor, wb: t
     return out, partial
 
 
+def pw_tf32(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, relu: bool = False,
+            transpose_w: bool = True, M: Optional[int] = None) -> torch.Tensor:
+    """fp32 pointwise conv on the tcgen05 tensor cores (3xTF32 split, x3d_pw_tf32_fwd).
+    `w` is the stored [K, N] fp32 kernel.  transpose_w=True: D[M, N] = a[M, K] . w (forward);
+    transpose_w=False: D[M, K] = a[M, N] . w^T (backward-data) -- no transposed copy is made either way:
+    x3d_tf32_split writes the hi / lo planes in the orientation the GEMM reads."""
+    _req(a, "a")
+    _req(w, "w")
+    if a.dtype != torch.float32 or w.dtype != torch.float32:
+        raise TypeError("pw_tf32 needs fp32 operands")
+    K, N = w.shape
+    red, nout = (K, N) if transpose_w else (N, K)
+    M = a.shape[0] if M is None else M
+    lda = a.shape[-1]
+    if lda < red:
+        raise ValueError(f"a has {lda} columns, the reduction needs {red}")
+    bs = torch.empty((2, nout, red), dtype=torch.float32, device=a.device)
+    _launch("x3d_tf32_split", lambda: lib().x3d_tf32_split(w.data_ptr(), bs.data_ptr(), nout, red, N,
+                                                         1 if transpose_w else 0, _stream()))
+    out = torch.empty((M, nout), dtype=torch.float32, device=a.device)
+    _launch("x3d_pw_tf32_fwd", lambda: lib().x3d_pw_tf32_fwd(a.data_ptr(), bs.data_ptr(), _ptr(bias), out.data_ptr(),
+                                                           M, red, nout, lda, nout, 1 if relu else 0, _stream()))
+    return out
+
+
 def expand_dw2_supported(T: int, H: int, W: int, cin: int, c: int, stride: int) -> int:
     """SE partial blocks per clip of the persistent fused kernel's plan, 0 if no tile plan fits."""
     return int(lib().x3d_expand_dw2_partial_blocks(T, H, W, cin, c, stride))

@@ -81,6 +81,10 @@ class X3DTrainer:
             raise NotImplementedError(f"{self.optimizer} not supported")
         self.adam = (0.9, 0.999, 1e-7)
         self.seed, self.iteration = seed, 0
+        # fp32 pointwise GEMMs (forward / backward-data): "tcgen05" = kind::tf32 MMA with the 3xTF32 split
+        # (x3d_pw_tf32_fwd); "mma_sync" = the legacy-path kernel of round 1 (x3d_pw_fwd).  X3D_TRAIN_GEMM overrides.
+        import os as _os
+        self.gemm = _os.environ.get("X3D_TRAIN_GEMM", "tcgen05")
         self.fixed_dropout_mask: Optional[torch.Tensor] = None      # tests inject a mask
         self.relu_masks: Optional[list] = None                      # tests: record every ReLU's sign pattern
         ar = self.arch
@@ -261,6 +265,9 @@ class X3DTrainer:
     # ------------------------------------------------------------------ primitive ops
     def _pw(self, x2d, w, bias=None, relu=False, gather=None, M=None):
         K, N = w.shape
+        if gather is None and self.gemm == "tcgen05":
+            # tcgen05.mma kind::tf32, 3xTF32 split (csrc/x3d_pw_tf32_tc.cu)
+            return ops.pw_tf32(x2d, w, bias, relu=relu, transpose_w=True, M=M)
         return ops.pw_fwd(x2d, w, bias, M=M if M is not None else x2d.shape[0], K=K, Nc=N,
                           out_dtype=torch.float32, relu=relu, gather=gather)
 
@@ -274,6 +281,8 @@ class X3DTrainer:
                                  _s()), "x3d_pw_wgrad")
         if not need_dx:
             return None
+        if self.gemm == "tcgen05":
+            return ops.pw_tf32(dy2d, w, None, transpose_w=False, M=M)       # dx = dy . w^T, w read as stored
         return ops.pw_fwd(dy2d, w.t().contiguous(), None, M=M, K=N, Nc=K, out_dtype=torch.float32)
 
     def _bias_grad(self, dy2d, name):
