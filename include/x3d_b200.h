@@ -98,6 +98,9 @@ int x3d_pw_fwd(const x3d_pw_args* args, void* stream);
  * a / c / shortcut / conv5 / fc1 / fc2, model.py:246-253, 292-299, 360-367, 78-108, and their
  * backward-data):   D[M, Nc] = act(bias + A[M, K] . B^T)
  *   A [M, lda] fp32, K % 4 == 0;  D [M, ldd] fp32, Nc % 4 == 0;  bias [Nc] fp32 or NULL;  relu 0/1
+ *   stats: NULL, or fp64 [2][Nc] (caller-zeroed) that receives += column sums and sums of squares of
+ *   D -- the batch statistics of the BatchNormalization that follows the conv (model.py:254,300,89),
+ *   accumulated in the epilogue instead of by a second pass over D (bias must be NULL, relu 0)
  *   Bsplit fp32 [2][Nc][K]: plane 0 = B rounded to TF32, plane 1 = B - plane 0 (B = the [Nc, K]
  *   operand with the reduction dimension contiguous), produced by
  * x3d_tf32_split(W, out, rows, cols, ld, transpose): out[.][r][c] from W[r*ld + c], or from
@@ -105,7 +108,7 @@ int x3d_pw_fwd(const x3d_pw_args* args, void* stream);
  *   backward-data: the same kernel as stored, rows = K, cols = Nc). */
 int x3d_tf32_split(const float* W, float* out, int rows, int cols, int ld, int transpose, void* stream);
 int x3d_pw_tf32_fwd(const float* A, const float* Bsplit, const float* bias, float* D, int64_t M, int K,
-                    int Nc, int lda, int ldd, int relu, void* stream);
+                    int Nc, int lda, int ldd, int relu, double* stats, void* stream);
 
 /* ---- Channelwise 3x3x3 convolution: Bottleneck.b + bn_b, model.py:309-310 -------------------
  * Grouped Conv3D(groups=C) stride (1,s,s), TF padding='same' (T: 1 before; H/W: pad_h/pad_w

@@ -50,7 +50,7 @@ SIGNATURES = {
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "x3d_pw_fwd": (C.c_int, [C.POINTER(PwArgs), C.c_void_p]),
     "x3d_tf32_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "x3d_pw_tf32_fwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_int] * 5 + [C.c_void_p]),
+    "x3d_pw_tf32_fwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "x3d_dw_partial_blocks": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "x3d_dw3x3x3_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

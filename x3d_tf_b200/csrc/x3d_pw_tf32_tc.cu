@@ -102,6 +102,7 @@ __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& l
 
 struct Params {
   const float* bias;
+  double* stats;   // [2][Nc] column sums / sums of squares of D (BatchNorm batch statistics), or nullptr
   long M;
   int Nc;          // output columns
   int NT;          // N tile (multiple of 32, <= 256)
@@ -269,6 +270,27 @@ pw_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tma_store_2d(&tmD, out_s + (sub_ctr & 1) * kATile, n0 + sb * 32, static_cast<int>(tile * kBlockM));
           tma_store_commit();
         }
+        if (p.stats != nullptr) {
+          // BatchNorm statistics of the layer this GEMM feeds (model.py:254,300,89 in training mode),
+          // taken from the staged tile while the TMA store reads it: thread = (column, 32-row group);
+          // rows past M are exact zeros (zero-filled A rows, no bias), so they add nothing
+          const int c = lane, rg = warp - 2;
+          const int col = n0 + sb * 32 + c;
+          const uint32_t cbase = out_s + (sub_ctr & 1) * kATile + static_cast<uint32_t>(c & 3) * 4;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int r = rg * 32 + i;
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(cbase + r * 128 + ((static_cast<uint32_t>(c >> 2) ^ static_cast<uint32_t>(r & 7)) << 4)));
+            s1 += v;
+            s2 = fmaf(v, v, s2);
+          }
+          if (col < p.Nc) {
+            atomicAdd(p.stats + col, static_cast<double>(s1));
+            atomicAdd(p.stats + p.Nc + col, static_cast<double>(s2));
+          }
+        }
       }
     }
     if (leader) tma_store_wait_read<0>();
@@ -337,8 +359,10 @@ extern "C" int x3d_tf32_split(const float* W, float* out, int rows, int cols, in
 }
 
 extern "C" int x3d_pw_tf32_fwd(const float* A, const float* Bsplit, const float* bias, float* D, int64_t M, int K,
-                               int Nc, int lda, int ldd, int relu, void* stream) {
+                               int Nc, int lda, int ldd, int relu, double* stats, void* stream) {
   X3D_REQUIRE(A && Bsplit && D, X3D_ERR_INVALID_ARG, "x3d_pw_tf32_fwd: null pointer");
+  X3D_REQUIRE(!stats || (!bias && !relu), X3D_ERR_INVALID_ARG,
+              "x3d_pw_tf32_fwd: column statistics are those of the plain product (no bias, no ReLU)");
   X3D_REQUIRE(M > 0 && M < (1L << 31), X3D_ERR_INVALID_ARG, "x3d_pw_tf32_fwd: M out of range");
   X3D_REQUIRE(K > 0 && K % 4 == 0 && lda % 4 == 0 && lda >= K, X3D_ERR_INVALID_ARG,
               "x3d_pw_tf32_fwd: K=%d / lda=%d must be multiples of 4", K, lda);
@@ -395,7 +419,7 @@ extern "C" int x3d_pw_tf32_fwd(const float* A, const float* Bsplit, const float*
     X3D_REQUIRE(r == CUDA_SUCCESS, X3D_ERR_LAUNCH, "x3d_pw_tf32_fwd: tensor map for D failed (%d; Nc=%d M=%ld ldd=%d)", (int)r, Nc, (long)M, ldd);
   }
   tf32tc::Params p;
-  p.bias = bias; p.M = M; p.Nc = Nc; p.NT = NT; p.KC = KC; p.k8_last = k8_last; p.stages = stages;
+  p.bias = bias; p.stats = stats; p.M = M; p.Nc = Nc; p.NT = NT; p.KC = KC; p.k8_last = k8_last; p.stages = stages;
   p.stage_bytes = stage_bytes; p.tmem_cols = tmem_cols; p.relu = relu;
   const size_t smem = (size_t)fixed + (size_t)stages * stage_bytes;
   const long num_tiles = (M + tf32tc::kBlockM - 1) / tf32tc::kBlockM;

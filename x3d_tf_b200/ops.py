@@ -276,11 +276,12 @@ def expand_dw_fwd(x: torch.Tensor, wa: torch.Tensor, bias_a: torch.Tensor, wb: t
 
 
 def pw_tf32(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, relu: bool = False,
-            transpose_w: bool = True, M: Optional[int] = None) -> torch.Tensor:
+            transpose_w: bool = True, M: Optional[int] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 pointwise conv on the tcgen05 tensor cores (3xTF32 split, x3d_pw_tf32_fwd).
     `w` is the stored [K, N] fp32 kernel.  transpose_w=True: D[M, N] = a[M, K] . w (forward);
     transpose_w=False: D[M, K] = a[M, N] . w^T (backward-data) -- no transposed copy is made either way:
-    x3d_tf32_split writes the hi / lo planes in the orientation the GEMM reads."""
+    x3d_tf32_split writes the hi / lo planes in the orientation the GEMM reads.  `stats`: zeroed fp64
+    [2, N] that receives the column sums / sums of squares of the result (BatchNorm batch statistics)."""
     _req(a, "a")
     _req(w, "w")
     if a.dtype != torch.float32 or w.dtype != torch.float32:
@@ -296,7 +297,8 @@ def pw_tf32(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
                                                          1 if transpose_w else 0, _stream()))
     out = torch.empty((M, nout), dtype=torch.float32, device=a.device)
     _launch("x3d_pw_tf32_fwd", lambda: lib().x3d_pw_tf32_fwd(a.data_ptr(), bs.data_ptr(), _ptr(bias), out.data_ptr(),
-                                                           M, red, nout, lda, nout, 1 if relu else 0, _stream()))
+                                                           M, red, nout, lda, nout, 1 if relu else 0, _ptr(stats),
+                                                           _stream()))
     return out
 
 

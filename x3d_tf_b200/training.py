@@ -153,6 +153,9 @@ class X3DTrainer:
                 self._bucket_of_stage[st] = next(i for i, (lo, hi) in enumerate(buckets)
                                                  if lo == self.layout.slots[first][0])
         self.exchange = GradientExchange(self.g, buckets, world, process_group)
+        # BatchNorm batch statistics of one step: fp64 [2, C] per BN layer, zeroed once per step
+        self._stat_arena = torch.zeros(2 * sum(_pad8(c) for c in self._bn_channels()), dtype=torch.float64, device=dev)
+        self._stat_used = 0
         self._converted: list = []
         for name in self.layout.slots:
             if self.decay[name]:
@@ -164,6 +167,17 @@ class X3DTrainer:
             self.moving[pfx + "/moving_variance"] = torch.ones(cs, dtype=torch.float32, device=dev)
 
     # ------------------------------------------------------------------ weights in / out
+    def _bn_channels(self):
+        ar = self.arch
+        yield ar.stem_channels
+        for b in ar.blocks:
+            if b.has_shortcut:
+                yield b.cout
+            yield b.cinner
+            yield b.cinner
+            yield b.cout
+        yield ar.conv5_channels
+
     def P(self, name: str) -> torch.Tensor:
         return self.layout.view(self.w, name)
 
@@ -263,11 +277,17 @@ class X3DTrainer:
         return st
 
     # ------------------------------------------------------------------ primitive ops
-    def _pw(self, x2d, w, bias=None, relu=False, gather=None, M=None):
+    def _pw(self, x2d, w, bias=None, relu=False, gather=None, M=None, stats=None):
+        """`stats`: None, or a zeroed fp64 [2, N] slice that the GEMM epilogue fills with the column sums /
+        sums of squares of the result (the following BatchNorm's batch statistics); returns (y, filled)."""
         K, N = w.shape
         if gather is None and self.gemm == "tcgen05":
             # tcgen05.mma kind::tf32, 3xTF32 split (csrc/x3d_pw_tf32_tc.cu)
-            return ops.pw_tf32(x2d, w, bias, relu=relu, transpose_w=True, M=M)
+            y = ops.pw_tf32(x2d, w, bias, relu=relu, transpose_w=True, M=M, stats=stats)
+            return y if stats is None else (y, True)
+        if stats is not None:
+            return ops.pw_fwd(x2d, w, bias, M=M if M is not None else x2d.shape[0], K=K, Nc=N,
+                              out_dtype=torch.float32, relu=relu, gather=gather), False
         return ops.pw_fwd(x2d, w, bias, M=M if M is not None else x2d.shape[0], K=K, Nc=N,
                           out_dtype=torch.float32, relu=relu, gather=gather)
 
@@ -290,11 +310,23 @@ class X3DTrainer:
         check(lib().x3d_colreduce(dy2d.data_ptr(), None, None, None, None, M, C, M,
                                   self.G64(name).data_ptr(), 2, _s()), "x3d_colreduce")
 
-    def _bn_fwd(self, x2d, prefix, relu, tape):
+    def _stat_slot(self, C: int) -> torch.Tensor:
+        """A zeroed fp64 [2, C] slice of the per-step statistics arena (one memset per step instead of
+        one fill kernel per BatchNorm)."""
+        n = 2 * C
+        if self._stat_used + n > self._stat_arena.numel():
+            return torch.zeros((2, C), dtype=torch.float64, device=self.device)
+        t = self._stat_arena[self._stat_used:self._stat_used + n].view(2, C)
+        self._stat_used += n
+        return t
+
+    def _bn_fwd(self, x2d, prefix, relu, tape, sums=None):
+        """`sums`: the batch statistics if the producing GEMM's epilogue already accumulated them."""
         M, C = x2d.shape
-        sums = torch.zeros((2, C), dtype=torch.float64, device=x2d.device)
-        check(lib().x3d_colreduce(x2d.data_ptr(), None, None, None, None, M, C, M, sums.data_ptr(), 0, _s()),
-              "x3d_colreduce")
+        if sums is None:
+            sums = self._stat_slot(C)
+            check(lib().x3d_colreduce(x2d.data_ptr(), None, None, None, None, M, C, M, sums.data_ptr(), 0, _s()),
+                  "x3d_colreduce")
         mean, var, rstd = (torch.empty(C, dtype=torch.float32, device=x2d.device) for _ in range(3))
         check(lib().x3d_bn_finalize(sums.data_ptr(), M, C, self.eps, self.bn_momentum, mean.data_ptr(),
                                     var.data_ptr(), rstd.data_ptr(),
@@ -341,6 +373,8 @@ class X3DTrainer:
         x = clips.contiguous()
         N, T, H, W, _ = x.shape
         self.g64.zero_()
+        self._stat_arena.zero_()
+        self._stat_used = 0
         tape: List = []                       # backward closures, each maps dy -> dx of its op
         self._exchange_started = False
 
@@ -379,9 +413,10 @@ class X3DTrainer:
         Nn, Tt, Hh, Ww, cl = act.shape
         P5 = Tt * Hh * Ww
         x5 = act.view(-1, cl)
-        y5 = self._pw(x5, self.P("conv5/layer_with_weights-0/kernel"))
+        st5 = self._stat_slot(_pad8(ar.conv5_channels))
+        y5, ok5 = self._pw(x5, self.P("conv5/layer_with_weights-0/kernel"), stats=st5)
         tape.append(lambda dy, x5=x5: self._pw_bwd(x5, dy, "conv5/layer_with_weights-0/kernel"))
-        a5 = self._bn_fwd(y5, "conv5/layer_with_weights-1", True, tape)
+        a5 = self._bn_fwd(y5, "conv5/layer_with_weights-1", True, tape, sums=st5 if ok5 else None)
         c5 = a5.shape[1]
         pool = ops.avgpool_fwd(a5.view(Nn, P5, c5))
 
@@ -457,9 +492,10 @@ class X3DTrainer:
         tape.append(split_bwd)
 
         # ---- main branch: a -> bn_a -> relu
-        a_pre = self._pw(x2, self.P(q + "/a/kernel"))
+        st_a = self._stat_slot(ci)                       # bn_a's batch statistics come out of the GEMM epilogue
+        a_pre, ok_a = self._pw(x2, self.P(q + "/a/kernel"), stats=st_a)
         tape.append(lambda dy: self._pw_bwd(x2, dy, q + "/a/kernel"))
-        a_out = self._bn_fwd(a_pre, q + "/bn_a", True, tape).view(N, T, H, W, ci)
+        a_out = self._bn_fwd(a_pre, q + "/bn_a", True, tape, sums=st_a if ok_a else None).view(N, T, H, W, ci)
         # ---- b (channelwise 3x3x3, SAME) -> bn_b
         wb = self.P(q + "/b/kernel")
         zero_b = torch.zeros(ci, dtype=torch.float32, device=x.device)
@@ -527,9 +563,10 @@ class X3DTrainer:
             return dy
         tape.append(se_swish_bwd)
         # ---- c -> bn_c
-        c_pre = self._pw(sw, self.P(q + "/c/kernel"))
+        st_c = self._stat_slot(co)
+        c_pre, ok_c = self._pw(sw, self.P(q + "/c/kernel"), stats=st_c)
         tape.append(lambda dy: self._pw_bwd(sw, dy, q + "/c/kernel"))
-        c_out = self._bn_fwd(c_pre, q + "/bn_c", False, tape)
+        c_out = self._bn_fwd(c_pre, q + "/bn_c", False, tape, sums=st_c if ok_c else None)
         # ---- shortcut (model.py:386-389) and add + relu (:389-392)
         if b.has_shortcut:
             gather = (T, Ho, Wo, H, W, s)
