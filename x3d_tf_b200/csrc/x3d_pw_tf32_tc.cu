@@ -230,14 +230,21 @@ pw_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t bias_s = smem_u32(sBias);
     uint32_t sub_ctr = 0;
     long it = 0;
+    // running column sums / sums of squares of this thread's (column, 32-row group) over all tiles of the
+    // CTA: one pair of global atomics per column and CTA at the end, not per tile (12.5 k tiles hitting
+    // the same 56 addresses measured +4 ms per step)
+    double acc1[8], acc2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc1[i] = acc2[i] = 0.0;
     for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = static_cast<int>(it & 1);
       const uint32_t aph = static_cast<uint32_t>((it >> 1) & 1);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.NT);
       mbar_wait(&t_full[as], aph);
       tcgen05_after_sync();
-      for (int sb = 0; sb < n_sub; ++sb, ++sub_ctr) {
-        if (n0 + sb * 32 >= p.Nc) break;          // uniform across the CTA
+#pragma unroll
+      for (int sb = 0; sb < 8; ++sb) {
+        if (sb >= n_sub || n0 + sb * 32 >= p.Nc) break;          // uniform across the CTA
         const uint32_t buf = out_s + (sub_ctr & 1) * kATile + sw_row;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -275,7 +282,6 @@ pw_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // taken from the staged tile while the TMA store reads it: thread = (column, 32-row group);
           // rows past M are exact zeros (zero-filled A rows, no bias), so they add nothing
           const int c = lane, rg = warp - 2;
-          const int col = n0 + sb * 32 + c;
           const uint32_t cbase = out_s + (sub_ctr & 1) * kATile + static_cast<uint32_t>(c & 3) * 4;
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll 8
@@ -286,14 +292,23 @@ pw_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             s1 += v;
             s2 = fmaf(v, v, s2);
           }
-          if (col < p.Nc) {
-            atomicAdd(p.stats + col, static_cast<double>(s1));
-            atomicAdd(p.stats + p.Nc + col, static_cast<double>(s2));
-          }
+          acc1[sb] += static_cast<double>(s1);
+          acc2[sb] += static_cast<double>(s2);
         }
+        ++sub_ctr;
       }
     }
     if (leader) tma_store_wait_read<0>();
+    if (p.stats != nullptr) {
+#pragma unroll
+      for (int sb = 0; sb < 8; ++sb) {
+        const int col = n0 + sb * 32 + lane;
+        if (sb < n_sub && col < p.Nc) {
+          atomicAdd(p.stats + col, acc1[sb]);
+          atomicAdd(p.stats + p.Nc + col, acc2[sb]);
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------------ transform: A -> (hi, lo)
     const int tt = threadIdx.x - (64 + 32 * kEpiWarps);        // 0..255
