@@ -211,6 +211,13 @@ int x3d_expand_dw2_fwd(const void* x, const void* wa, const float* bias_a, const
  * in [pixels,3] uint8 (4-byte aligned) -> out [pixels,3] fp32 or bf16 (16-byte aligned). */
 int x3d_normalize_u8(const uint8_t* in, void* out, int64_t pixels, const float* mean,
                      const float* std, float norm_value, int dtype, void* stream);
+/* Evaluation clips of one decoded, already resized video, on the device: temporal views
+ * (transforms.py:48-65: frame ((view*T + t) * max(1, F/T)) mod F, the video looped as often as
+ * needed) and uniform spatial crops (transforms.py:149-190, 216-222: centre, or left / centre / right
+ * along the longer side, offsets ceil((dim - S) / 2)), in the clip order dataloader.py:107-116 hands
+ * to the model:   video [F,H,W,3] uint8 -> out [crops*views, T, S, S, 3] uint8 (crop-major). */
+int x3d_eval_views_u8(const uint8_t* video, uint8_t* out, int F, int H, int W, int T, int views,
+                      int crops, int S, void* stream);
 /* x3d_stem_tc_fwd with the input stage fused into its loader: uint8 NDHWC clips in, bf16
  * activations out (same result as x3d_normalize_u8(bf16) followed by x3d_stem_tc_fwd). */
 int x3d_stem_tc_u8_fwd(const uint8_t* in, const float* mean, const float* std, float norm_value,

@@ -42,3 +42,37 @@ def eval_metrics(probs: np.ndarray, labels: np.ndarray, k: int = 5) -> dict:
     return {"loss": float(loss.astype(np.float64).mean()), "acc": float(top1.mean()),
             f"top_{k}_acc": float(topk.mean()), "videos": V,
             "sums": np.array([loss.astype(np.float64).sum(), top1.sum(), topk.sum(), V], np.float64)}
+
+
+def eval_views(video: np.ndarray, T: int, views: int, crops: int, size: int) -> np.ndarray:
+    """Evaluation clips of one decoded, resized video [F,H,W,C] as the reference builds them
+    (parity unpinned against TensorFlow; restated line by line):
+      * temporal (transforms.py:48-65): sample_rate = max(1, F // T); end = T * sample_rate * views;
+        indices = tile(range(F), loops)[0:end][0:end:sample_rate]; reshape to [views, T, ...];
+      * spatial (transforms.py:149-190, 216-222): crop i of `crops` uses spatial_idx = i % 3 if
+        crops > 1 else 1; offsets ceil((dim - size) / 2), the longer side gets 0 / dim - size for
+        idx 0 / 2 (`if height > width` ... `else` ...);
+      * batching (dataloader.py:107-116): [crops, views, T, S, S, C] reshaped to [-1, T, S, S, C]."""
+    F, H, W, _ = video.shape
+    rate = max(1, F // T)
+    end = T * rate * views
+    loops = -(-end // F)
+    idx = np.tile(np.arange(F), loops)[0:end][0:end:rate]
+    clip = video[idx].reshape(views, T, H, W, video.shape[3])
+    out = []
+    for i in range(crops):
+        sidx = i % 3 if crops > 1 else 1
+        y0 = int(np.ceil((H - size) / 2))
+        x0 = int(np.ceil((W - size) / 2))
+        if H > W:
+            if sidx == 0:
+                y0 = 0
+            elif sidx == 2:
+                y0 = H - size
+        else:
+            if sidx == 0:
+                x0 = 0
+            elif sidx == 2:
+                x0 = W - size
+        out.append(clip[:, :, y0:y0 + size, x0:x0 + size, :])
+    return np.stack(out).reshape(-1, T, size, size, video.shape[3])

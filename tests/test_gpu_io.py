@@ -153,3 +153,20 @@ def test_eval_driver_finds_checkpoint_and_evaluates(tmp_path, capsys):
     empty = tmp_path / "empty"
     empty.mkdir()
     assert E.run(["--cfg", "X3D_XS", "--model_folder", str(empty), "--synthetic", "3"]) is None
+
+
+@pytest.mark.parametrize("F,H,W,T,views,crops,S", [(40, 20, 28, 4, 2, 3, 20), (7, 33, 21, 4, 3, 3, 21),
+                                                   (100, 16, 16, 13, 1, 1, 16), (5, 24, 19, 16, 10, 1, 18),
+                                                   (64, 182, 242, 13, 2, 3, 182)])
+def test_eval_views_u8_is_bit_exact(F, H, W, T, views, crops, S):
+    """x3d_eval_views_u8 == the reference's temporal views + uniform crops + batch reshape
+    (transforms.py:48-65, 149-222; dataloader.py:107-116), byte for byte: short videos that loop,
+    more views than frames, landscape and portrait frames, one and three crops, odd row lengths."""
+    from oracle import io_oracle
+    from x3d_tf_b200 import ops
+    rng = np.random.default_rng(F + H + W)
+    video = rng.integers(0, 256, size=(F, H, W, 3), dtype=np.uint8)
+    want = io_oracle.eval_views(video, T, views, crops, S)
+    got = ops.eval_views_u8(torch.from_numpy(video).cuda(), T, views, crops, S)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and np.array_equal(got.cpu().numpy(), want)

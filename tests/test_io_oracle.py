@@ -114,3 +114,26 @@ def test_metric_sums_reduce_over_ranks_gloo():
     for r in range(2):
         assert res[r]["videos"] == 5
         assert abs(res[r]["loss"] - 6.5 / 5) < 1e-12 and res[r]["acc"] == 0.6 and res[r]["top_5_acc"] == 0.8
+
+
+def test_eval_views_oracle_hand_worked():
+    """transforms.py:48-65 / 149-222 on a video whose pixel value encodes (frame, y, x)."""
+    from oracle import io_oracle
+    F, H, W = 5, 4, 6
+    video = np.zeros((F, H, W, 1), np.int64)
+    for f in range(F):
+        for y in range(H):
+            for x in range(W):
+                video[f, y, x, 0] = f * 100 + y * 10 + x
+    # T=2, 3 views: rate = max(1, 5 // 2) = 2; frames (k*2) mod 5 for k = 0..5 -> 0,2,4,1,3,0
+    out = io_oracle.eval_views(video, T=2, views=3, crops=3, size=4)
+    assert out.shape == (9, 2, 4, 4, 1)
+    frames = out[:, :, 0, 0, 0] // 100
+    assert frames[:3].tolist() == [[0, 2], [4, 1], [3, 0]]            # crop 0: views 0..2
+    # landscape (W > H): x offsets 0, ceil((6-4)/2) = 1, 6-4 = 2 for left / centre / right; y offset 0
+    assert [int(out[c * 3, 0, 0, 0, 0] % 10) for c in range(3)] == [0, 1, 2]
+    assert int(out[0, 0, 0, 0, 0] // 10 % 10) == 0
+    one = io_oracle.eval_views(video, T=2, views=1, crops=1, size=4)   # single crop = centre
+    assert int(one[0, 0, 0, 0, 0] % 10) == 1
+    tall = io_oracle.eval_views(video.transpose(0, 2, 1, 3), T=2, views=1, crops=3, size=4)   # H > W: y offsets
+    assert [int(tall[c, 0, 0, 0, 0] // 100 * 0 + tall[c, 0, 0, 0, 0] % 10) for c in range(3)] == [0, 1, 2]

@@ -189,3 +189,20 @@ def test_pixel_pairing_host_logic():
         assert torch.equal(bias, torch.cat([a2.bias, a2.bias]))
     finally:
         M.Options.pair_pixels, M.Options.pair_aligned, M.Options.pair_max_k, M.Options.pair_max_n = saved
+
+
+def test_precision_policy_and_strategy_host_logic(monkeypatch):
+    """utils.get_precision / get_strategy (utils.py:144-192): policy names and the no-CPU rule."""
+    import torch
+    from x3d_tf_b200 import runtime as R
+    assert R.get_precision(False) == "float32"
+    assert R.get_precision(True) == ("mixed_bfloat16" if torch.cuda.is_available() else "float32")
+    assert R.policy_dtype("mixed_bfloat16") == "bfloat16" and R.policy_dtype("mixed_float16") == "bfloat16"
+    assert R.policy_dtype("float32") == "float32"
+    with pytest.raises(ValueError):
+        R.policy_dtype("float64")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            R.get_strategy(1)                       # the reference would fall back to the CPU; this build must not
+    st = R.Strategy(rank=1, world=2, device=torch.device("cpu"))
+    assert st.num_replicas_in_sync == 2 and st.shard(7) == (4, 7)

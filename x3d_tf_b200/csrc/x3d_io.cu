@@ -97,10 +97,76 @@ eval_metrics_kernel(const float* __restrict__ probs, const int32_t* __restrict__
   }
 }
 
+// Evaluation clips of one decoded video: temporal views (transforms.py:48-65) and uniform spatial
+// crops (transforms.py:149-190, 216-222) as ONE gather on the device.
+//   out[crop][view][t][y][x][c] = in[((view*T + t) * rate) mod F][y0(crop) + y][x0(crop) + x][c]
+// rate = max(1, F / T): the reference tiles the frame indices until T*rate*views of them exist and takes
+// every rate-th one; crop offsets: centre = ceil((dim - S) / 2); with three crops the longer side
+// gets 0 / centre / dim - S.  One thread copies 4 output bytes (a row of S*3 bytes is a contiguous
+// run of the input row; its start is not 4-byte aligned in general, hence byte loads).
+struct Views {
+  int F, H, W, T, views, crops, S;
+  int y0[3], x0[3];
+  int rate;
+};
+
+__global__ void __launch_bounds__(256)
+eval_views_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const Views v) {
+  const int64_t row_bytes = static_cast<int64_t>(v.S) * 3;
+  const int64_t rows = static_cast<int64_t>(v.crops) * v.views * v.T * v.S;
+  const int64_t total = rows * row_bytes;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
+  for (int64_t e = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; e < total; e += stride) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int64_t o = e + b;
+      if (o >= total) break;
+      const int64_t row = o / row_bytes;
+      const int xb = static_cast<int>(o - row * row_bytes);
+      const int y = static_cast<int>(row % v.S);
+      const int64_t r2 = row / v.S;
+      const int t = static_cast<int>(r2 % v.T);
+      const int64_t r3 = r2 / v.T;
+      const int view = static_cast<int>(r3 % v.views), crop = static_cast<int>(r3 / v.views);
+      const int f = static_cast<int>((static_cast<int64_t>(view) * v.T + t) * v.rate % v.F);
+      const int64_t src = ((static_cast<int64_t>(f) * v.H + v.y0[crop] + y) * v.W + v.x0[crop]) * 3 + xb;
+      w |= static_cast<uint32_t>(__ldg(in + src)) << (8 * b);
+    }
+    if (e + 4 <= total) *reinterpret_cast<uint32_t*>(out + e) = w;
+    else for (int b = 0; e + b < total; ++b) out[e + b] = static_cast<uint8_t>(w >> (8 * b));
+  }
+}
+
 }  // namespace io
 }  // namespace x3d
 
 using namespace x3d;
+
+extern "C" int x3d_eval_views_u8(const uint8_t* video, uint8_t* out, int F, int H, int W, int T, int views,
+                                 int crops, int S, void* stream) {
+  X3D_REQUIRE(video && out, X3D_ERR_INVALID_ARG, "x3d_eval_views_u8: null pointer");
+  X3D_REQUIRE(F > 0 && T > 0 && views > 0 && S > 0 && H >= S && W >= S, X3D_ERR_INVALID_ARG,
+              "x3d_eval_views_u8: bad extents F=%d T=%d views=%d S=%d H=%d W=%d", F, T, views, S, H, W);
+  X3D_REQUIRE(crops == 1 || crops == 3, X3D_ERR_INVALID_ARG, "x3d_eval_views_u8: crops=%d (1 or 3)", crops);
+  X3D_REQUIRE((reinterpret_cast<uintptr_t>(out) & 3) == 0, X3D_ERR_INVALID_ARG, "x3d_eval_views_u8: out must be 4-byte aligned");
+  io::Views v;
+  v.F = F; v.H = H; v.W = W; v.T = T; v.views = views; v.crops = crops; v.S = S;
+  v.rate = F / T > 1 ? F / T : 1;
+  const int yc = (H - S + 1) / 2, xc = (W - S + 1) / 2;                // ceil((dim - S) / 2)
+  for (int i = 0; i < 3; ++i) {
+    const int idx = crops > 1 ? i % 3 : 1;                             // left/centre/right vs centre
+    v.y0[i] = yc; v.x0[i] = xc;
+    if (H > W) { if (idx == 0) v.y0[i] = 0; else if (idx == 2) v.y0[i] = H - S; }
+    else       { if (idx == 0) v.x0[i] = 0; else if (idx == 2) v.x0[i] = W - S; }
+  }
+  const int64_t total = (int64_t)crops * views * T * S * S * 3;
+  int64_t blocks = (total / 4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  io::eval_views_u8_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(video, out, v);
+  return check_launch("x3d_eval_views_u8");
+}
 
 extern "C" int x3d_normalize_u8(const uint8_t* in, void* out, int64_t pixels, const float* mean,
                                 const float* std, float norm_value, int dtype, void* stream) {

@@ -539,20 +539,24 @@ gather_rows_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long r
 // Skinny GEMM for the head (fc1 + ReLU, fc2 + bias; model.py:119-121): M = clips (tens), so the
 // work is streaming the fp32 weights once.  CTA = 16 output columns x up to 128 rows; K is walked
 // in chunks of 64 staged in shared memory; thread = (column, row group of 8).
-constexpr int kSkN = 16, kSkK = 64, kSkRows = 8, kSkM = 16 * kSkRows;
+constexpr int kSkK = 64, kSkM = 128;
 
+// SKN output columns per CTA (16, or 4 when 16 would leave most SMs idle: fc2 has 400 columns and
+// K = 2048, i.e. 25 CTAs each walking 32 K chunks one after the other with the 16-column tile).
+template <int SKN>
 __global__ void __launch_bounds__(256)
 skinny_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
                    const float* __restrict__ bias, float* __restrict__ D, int M, int K, int Nc,
                    int lda, int ldw, int ldd, int relu) {
+  constexpr int kGroups = 256 / SKN, kRows = kSkM / kGroups;     // row groups, rows per thread
   __shared__ __align__(16) float As[kSkM][kSkK + 4];
-  __shared__ __align__(16) float Ws[kSkK][kSkN];
-  const int tid = threadIdx.x, c = tid & 15, g = tid >> 4;
-  const int n0 = blockIdx.x * kSkN, m0 = blockIdx.y * kSkM;
+  __shared__ __align__(16) float Ws[kSkK][SKN];
+  const int tid = threadIdx.x, c = tid % SKN, g = tid / SKN;
+  const int n0 = blockIdx.x * SKN, m0 = blockIdx.y * kSkM;
   const int rows = min(kSkM, M - m0);
-  float acc[kSkRows];
+  float acc[kRows];
 #pragma unroll
-  for (int i = 0; i < kSkRows; ++i) acc[i] = 0.f;
+  for (int i = 0; i < kRows; ++i) acc[i] = 0.f;
   for (int k0 = 0; k0 < K; k0 += kSkK) {
     __syncthreads();
     for (int i = tid; i < kSkM * (kSkK / 4); i += 256) {
@@ -561,8 +565,8 @@ skinny_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
       if (r < rows && k0 + kv < K) v = __ldg(reinterpret_cast<const float4*>(A + (long)(m0 + r) * lda + k0 + kv));
       *reinterpret_cast<float4*>(&As[r][kv]) = v;
     }
-    for (int i = tid; i < kSkK * (kSkN / 4); i += 256) {
-      const int k = i / (kSkN / 4), nv = (i - k * (kSkN / 4)) * 4;
+    for (int i = tid; i < kSkK * (SKN / 4); i += 256) {
+      const int k = i / (SKN / 4), nv = (i - k * (SKN / 4)) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (k0 + k < K && n0 + nv < Nc) v = __ldg(reinterpret_cast<const float4*>(Wt + (long)(k0 + k) * ldw + n0 + nv));
       *reinterpret_cast<float4*>(&Ws[k][nv]) = v;
@@ -572,8 +576,8 @@ skinny_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
     for (int k = 0; k < kSkK; k += 4) {
       const float w0 = Ws[k][c], w1 = Ws[k + 1][c], w2 = Ws[k + 2][c], w3 = Ws[k + 3][c];
 #pragma unroll
-      for (int i = 0; i < kSkRows; ++i) {
-        const float4 a = *reinterpret_cast<const float4*>(&As[g + 16 * i][k]);
+      for (int i = 0; i < kRows; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[g + kGroups * i][k]);
         acc[i] = fmaf(a.x, w0, acc[i]);
         acc[i] = fmaf(a.y, w1, acc[i]);
         acc[i] = fmaf(a.z, w2, acc[i]);
@@ -585,8 +589,8 @@ skinny_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
   if (col >= Nc) return;
   const float b = bias ? __ldg(bias + col) : 0.f;
 #pragma unroll
-  for (int i = 0; i < kSkRows; ++i) {
-    const int r = g + 16 * i;
+  for (int i = 0; i < kRows; ++i) {
+    const int r = g + kGroups * i;
     if (r < rows) {
       float y = acc[i] + b;
       if (relu) y = fmaxf(y, 0.f);
@@ -717,9 +721,15 @@ int x3d_head_fc_fwd(const float* A, const float* Wt, const float* bias, float* D
   X3D_REQUIRE(M > 0 && K > 0 && Nc > 0, X3D_ERR_INVALID_ARG, "x3d_head_fc_fwd: empty problem");
   X3D_REQUIRE(K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && Nc % 4 == 0, X3D_ERR_INVALID_ARG, "x3d_head_fc_fwd: K/lda/ldw/Nc must be multiples of 4");
   X3D_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Wt)) & 15) == 0, X3D_ERR_INVALID_ARG, "x3d_head_fc_fwd: pointers must be 16-byte aligned");
-  dim3 grid((Nc + kSkN - 1) / kSkN, (M + kSkM - 1) / kSkM);
-  X3D_REQUIRE(grid.y <= 65535, X3D_ERR_UNSUPPORTED, "x3d_head_fc_fwd: M too large");
-  skinny_gemm_kernel<<<grid, 256, 0, S(stream)>>>(A, Wt, bias, D, M, K, Nc, lda, ldw, ldd, relu);
+  const int my = (M + kSkM - 1) / kSkM;
+  X3D_REQUIRE(my <= 65535, X3D_ERR_UNSUPPORTED, "x3d_head_fc_fwd: M too large");
+  if ((long)((Nc + 15) / 16) * my < 96) {          // too few 16-column CTAs to cover the SMs: 4-column tiles
+    dim3 grid((Nc + 3) / 4, my);
+    skinny_gemm_kernel<4><<<grid, 256, 0, S(stream)>>>(A, Wt, bias, D, M, K, Nc, lda, ldw, ldd, relu);
+  } else {
+    dim3 grid((Nc + 15) / 16, my);
+    skinny_gemm_kernel<16><<<grid, 256, 0, S(stream)>>>(A, Wt, bias, D, M, K, Nc, lda, ldw, ldd, relu);
+  }
   return check_launch("x3d_head_fc_fwd");
 }
 

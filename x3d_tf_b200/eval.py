@@ -90,7 +90,11 @@ def run(argv: Optional[List[str]] = None) -> Optional[dict]:
     ap.add_argument("--model_folder", required=True, help="directory with a TF `checkpoint` file")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--synthetic", type=int, default=0, help="evaluate this many seeded random videos")
-    ap.add_argument("--dtype", default="bfloat16", choices=["bfloat16", "float32"])
+    ap.add_argument("--dtype", default=None, choices=["bfloat16", "float32"],
+                    help="activation storage; default: the --mixed_precision policy")
+    ap.add_argument("--mixed_precision", action="store_true", default=True,
+                    help="utils.get_precision: 16-bit activations (bfloat16 here, see runtime.py); --no_mixed_precision for fp32")
+    ap.add_argument("--no_mixed_precision", dest="mixed_precision", action="store_false")
     ap.add_argument("--allow_random_init", action="store_true",
                     help="run with freshly initialised weights when the folder has no checkpoint data")
     a = ap.parse_args(argv)
@@ -112,7 +116,8 @@ def run(argv: Optional[List[str]] = None) -> Optional[dict]:
 
     from .model import X3D, reset_block_counters
     reset_block_counters()
-    model = X3D(cfg, dtype=a.dtype).compile(top_k=5)
+    from .runtime import get_precision, policy_dtype
+    model = X3D(cfg, dtype=a.dtype or policy_dtype(get_precision(a.mixed_precision))).compile(top_k=5)
     ckpt = latest_checkpoint(a.model_folder)
     if ckpt:
         print(f"Found checkpoint {ckpt}", file=sys.stderr)

@@ -172,7 +172,11 @@ def _as_device_clip(x, device) -> torch.Tensor:
         raise TypeError("input must be a torch.Tensor or numpy array in NDHWC layout")
     if x.dim() != 5:
         raise ValueError(f"expected a 5-D NDHWC tensor, got shape {tuple(x.shape)}")
-    if x.dtype == torch.float16 or x.dtype == torch.float64:
+    if x.dtype == torch.float16:
+        # the reference's mixed_float16 input cast (dataloader.py:118-120): this build's 16-bit policy is
+        # bfloat16 (runtime.py); fp16 clips enter as bf16 (normalised pixels are within +-4: no range issue)
+        x = x.to(torch.bfloat16)
+    elif x.dtype == torch.float64:
         x = x.to(torch.float32)
     if x.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
         raise TypeError(f"unsupported input dtype {x.dtype}")

@@ -123,6 +123,19 @@ def normalize_u8(x: torch.Tensor, mean, std, out_dtype: torch.dtype, norm_value:
     return out
 
 
+def eval_views_u8(video: torch.Tensor, T: int, views: int, crops: int, size: int) -> torch.Tensor:
+    """Evaluation clips of one decoded, resized video [F,H,W,3] uint8 (device): temporal views
+    (transforms.py:48-65) x uniform crops (transforms.py:149-222) -> [crops*views, T, size, size, 3]."""
+    _req(video, "video")
+    if video.dtype != torch.uint8 or video.dim() != 4 or video.shape[-1] != 3:
+        raise TypeError("eval_views_u8 needs a [F,H,W,3] uint8 video")
+    F, H, W, _ = video.shape
+    out = torch.empty((crops * views, T, size, size, 3), dtype=torch.uint8, device=video.device)
+    _launch("x3d_eval_views_u8", lambda: lib().x3d_eval_views_u8(video.data_ptr(), out.data_ptr(), F, H, W, T, views,
+                                                               crops, size, _stream()))
+    return out
+
+
 def stem_tc_u8_fwd(x: torch.Tensor, mean, std, wc: torch.Tensor, bias: torch.Tensor,
                    norm_value: float = 255.0) -> torch.Tensor:
     """Tensor-core stem with the uint8 input stage fused into its loader; bf16 activations out."""

@@ -100,6 +100,9 @@ def run(argv: Optional[List[str]] = None) -> Optional[dict]:
     ap.add_argument("--steps_per_epoch", type=int, default=0, help="override DATASET_SIZE // BATCH_SIZE")
     ap.add_argument("--batch_size", type=int, default=0, help="override cfg.TRAIN.BATCH_SIZE (global batch)")
     ap.add_argument("--crop_size", type=int, default=0, help="override cfg.DATA.TRAIN_CROP_SIZE (synthetic data)")
+    ap.add_argument("--mixed_precision", action="store_true",
+                    help="train.py:26,72-74,99-100.  Not built: the training kernels compute in fp32 (the "
+                         "reference's default precision); the flag is rejected rather than ignored")
     a = ap.parse_args(argv)
     if not a.train_file_pattern and not a.synthetic:
         ap.error("one of --train_file_pattern / --synthetic is required")
@@ -107,6 +110,9 @@ def run(argv: Optional[List[str]] = None) -> Optional[dict]:
         cfg = get_default_config(); cfg.merge_from_file(a.config); cfg.freeze()
     else:
         cfg = get_config(a.config)
+    if a.mixed_precision:
+        raise NotImplementedError("--mixed_precision: the training step runs in fp32 only (no 16-bit backward "
+                                  "kernels, no loss scaling); evaluation has the 16-bit policy (eval --mixed_precision)")
     if cfg.TRAIN.OPTIMIZER.lower() not in ("sgd", "adam"):
         raise NotImplementedError(f"{cfg.TRAIN.OPTIMIZER} not supported")          # train.py:96-97
     os.makedirs(a.model_dir, exist_ok=True)
