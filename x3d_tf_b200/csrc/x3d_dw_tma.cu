@@ -219,18 +219,21 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     }
   };
 
-  for (int t = 0; t < p.T; t += 3) {
+  // Whole triples in the loop (after three steps the accumulator sets are back in their original
+  // roles, so they live in fixed registers: no rotation moves at the loop edge), T % 3 frames after it.
+  int t = 0;
+  for (; t + 3 <= p.T; t += 3) {
     step(t, acc[1], acc[0], acc[2]);
-    if (t + 1 < p.T) step(t + 1, acc[2], acc[1], acc[0]);
-    if (t + 2 < p.T) step(t + 2, acc[0], acc[2], acc[1]);
+    step(t + 1, acc[2], acc[1], acc[0]);
+    step(t + 2, acc[0], acc[2], acc[1]);
   }
+  const int rem = p.T - t;
+  if (rem >= 1) step(t, acc[1], acc[0], acc[2]);
+  if (rem == 2) step(t + 1, acc[2], acc[1], acc[0]);
   // the last output frame never sees a dt=2 contribution (temporal zero padding)
-  {
-    const int r = (p.T - 1) % 3;
-    if (r == 0) stage_out(acc[0], p.T - 1);
-    else if (r == 1) stage_out(acc[1], p.T - 1);
-    else stage_out(acc[2], p.T - 1);
-  }
+  if (rem == 0) stage_out(acc[2], p.T - 1);
+  else if (rem == 1) stage_out(acc[0], p.T - 1);
+  else stage_out(acc[1], p.T - 1);
   if (p.partial != nullptr && in_slot) {
     s_red[slot * CH + 2 * cp] = ssum.x;
     s_red[slot * CH + 2 * cp + 1] = ssum.y;
