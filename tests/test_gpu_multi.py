@@ -28,7 +28,19 @@ def _spawn(fn, world=2):
     q, port = ctx.Queue(), _free_port()
     procs = [ctx.Process(target=fn, args=(r, world, port, q)) for r in range(world)]
     [p.start() for p in procs]
-    out = dict(q.get(timeout=600) for _ in range(world))
+    out = {}
+    import queue as _queue
+    import time as _time
+    deadline = _time.time() + 300
+    while len(out) < world:
+        try:
+            k, v = q.get(timeout=5)
+            out[k] = v
+        except _queue.Empty:
+            dead = [p for p in procs if p.exitcode not in (None, 0)]
+            if dead or _time.time() > deadline:          # a crashed rank must fail the test, not hang it
+                [p.kill() for p in procs if p.is_alive()]
+                raise AssertionError(f"worker exit codes {[p.exitcode for p in procs]}")
     [p.join(120) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     return out

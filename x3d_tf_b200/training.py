@@ -153,6 +153,7 @@ class X3DTrainer:
                 self._bucket_of_stage[st] = next(i for i, (lo, hi) in enumerate(buckets)
                                                  if lo == self.layout.slots[first][0])
         self.exchange = GradientExchange(self.g, buckets, world, process_group)
+        self._exchange_in_backward = False
         # BatchNorm batch statistics of one step: fp64 [2, C] per BN layer, zeroed once per step
         self._stat_arena = torch.zeros(2 * sum(_pad8(c) for c in self._bn_channels()), dtype=torch.float64, device=dev)
         self._stat_used = 0
@@ -376,7 +377,6 @@ class X3DTrainer:
         self._stat_arena.zero_()
         self._stat_used = 0
         tape: List = []                       # backward closures, each maps dy -> dx of its op
-        self._exchange_started = False
 
         # ---- stem (model.py:202-208)
         cs = _pad8(ar.stem_channels)
@@ -403,7 +403,7 @@ class X3DTrainer:
 
         # ---- residual stages (model.py:384-394, 305-320)
         for b in ar.blocks:
-            if self.world > 1 and b.index == 0 and b.stage in self._bucket_of_stage:
+            if self.world > 1 and self._exchange_in_backward and b.index == 0 and b.stage in self._bucket_of_stage:
                 # replayed AFTER every backward closure of this stage and of everything behind it: the
                 # gradients of the bucket that starts at this stage are complete -> start its all-reduce
                 tape.append(lambda d, k=self._bucket_of_stage[b.stage]: self._bucket_ready(k, d))
@@ -608,7 +608,11 @@ class X3DTrainer:
     def step(self, clips: torch.Tensor, labels: torch.Tensor, lr: float) -> torch.Tensor:
         """forward + backward + gradient all-reduce + SGD-Nesterov update.  Returns per-clip losses."""
         self._converted = []
-        loss = self.forward_backward(clips, labels)
+        self._exchange_in_backward = True       # only step() communicates; forward_backward alone never does
+        try:
+            loss = self.forward_backward(clips, labels)
+        finally:
+            self._exchange_in_backward = False
         n = self.layout.size
         if self.world > 1:
             # buckets whose all-reduce already runs behind the backward pass are done; the rest (the
