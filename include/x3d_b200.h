@@ -131,6 +131,20 @@ int x3d_dw3x3x3_act_fwd(const void* in, const float* w, const float* bias, void*
                         float* se_partial, int N, int T, int H, int W, int C, int stride,
                         int pad_h, int pad_w, int dtype, int act, void* stream);
 
+/* The same layer (model.py:309-316; bf16 only) with lanes = pixels and warp = channel pair, so that the
+ * 27 taps sit in uniform registers and the packed FFMA2 reads two register operands instead of three
+ * (csrc/x3d_dw_planar.cu).  `taps`: device fp32 [ceil(C/2)][28][2] = per channel pair the 27 BN-folded
+ * taps (dt, dh, dw major) and the BN shift, as (channel 2p, channel 2p+1); copied into the constant
+ * bank, stream-ordered, by the call.  C <= 576.  se_partial [N, nblk, C], nblk =
+ * x3d_dw_planar_partial_blocks(...); act as for x3d_dw3x3x3_act_fwd.  The tap table is one per device:
+ * calls on ONE stream (or stream-ordered against each other) only.
+ * x3d_dw_planar_lane_permille: output pixels / (pixels of the tiles that cover them) * 1000, i.e. how
+ * much of the kernel's lane grid a shape uses (1000 at 64x64, 875 at 56x56); 0 = no plan. */
+int x3d_dw_planar_partial_blocks(int T, int H, int W, int C, int stride);
+int x3d_dw_planar_lane_permille(int T, int H, int W, int C, int stride);
+int x3d_dw3x3x3_planar_fwd(const void* in, const float* taps, void* out, float* se_partial, int N, int T,
+                           int H, int W, int C, int stride, int pad_h, int pad_w, int act, void* stream);
+
 /* ---- Squeeze-Excitation MLP: se_pool/se_fc1/se_fc2, model.py:311-314 ------------------------
  *   mean[n,c] = inv_count * sum_b partial[n,b,c];  z = relu(mean.w1 + b1);  scale = sigmoid(z.w2 + b2)
  *   w1 [C,Cw], b1 [Cw], w2 [Cw,C], b2 [C] fp32;  scale [N,C] fp32.   Cw <= 64. */

@@ -111,6 +111,36 @@ def test_channelwise(dtype, N, T, H, W, C, stride):
         _ops().dw_fwd(to_dev(x, dtype), to_dev(k.reshape(27, C)), to_dev(bias), stride, ph, pw, True, swish=True)
 
 
+@pytest.mark.parametrize("N,T,H,W,C,stride", DW_CASES + [(3, 4, 64, 64, 56, 1), (2, 16, 33, 70, 24, 1), (2, 5, 64, 64, 56, 2),
+                                                        (5, 3, 8, 8, 432, 1), (2, 7, 16, 16, 216, 2)])
+def test_channelwise_planar(N, T, H, W, C, stride):
+    """x3d_dw3x3x3_planar_fwd (lanes = pixels, taps in uniform registers) against the same oracle as
+    x3d_dw3x3x3_fwd: output, SE partial sums, swish epilogue; several clips / tiles / chunks per CTA."""
+    from x3d_tf_b200.arch import same_pad
+    ops = _ops()
+    if ops.dw_planar_supported(T, H, W, C, stride) <= 0:
+        pytest.skip("planar kernel does not take this width (C > 576)")
+    dtype = torch.bfloat16
+    rng = np.random.default_rng(H * 100 + W + C + stride)
+    x = _q(rng.normal(size=(N, T, H, W, C)), dtype)
+    k = rng.normal(size=(3, 3, 3, 1, C)).astype(np.float32) * 0.3
+    bias = rng.normal(size=C).astype(np.float32) * 0.2
+    want = np_ops.channelwise_conv_same(x, k, stride) + bias
+    _, ph, _ = same_pad(H, 3, stride)
+    _, pw, _ = same_pad(W, 3, stride)
+    taps = ops.dw_planar_taps(to_dev(k.reshape(27, C)), to_dev(bias))
+    out, partial = ops.dw_planar_fwd(to_dev(x, dtype), taps, stride, ph, pw, True)
+    torch.cuda.synchronize()
+    assert_close(to_np(out), want, dtype, "planar channelwise")
+    sums = to_np(partial).astype(np.float64).sum(1)
+    np.testing.assert_allclose(sums, want.sum((1, 2, 3)), rtol=2e-4,
+                               atol=2e-4 * np.abs(want).sum((1, 2, 3)).max())
+    out2, p2 = ops.dw_planar_fwd(to_dev(x, dtype), taps, stride, ph, pw, False)
+    assert p2 is None and torch.equal(out, out2)
+    out3, _ = ops.dw_planar_fwd(to_dev(x, dtype), taps, stride, ph, pw, False, swish=True)
+    assert_close(to_np(out3), want / (1.0 + np.exp(-want)), dtype, "planar channelwise + swish")
+
+
 # ------------------------------------------------------------------------------- fused expand + channelwise
 AB_CASES = [  # N, T, H, W, Cin, C, stride  -- every stage shape class, odd extents, both pads, K > 64
     (2, 4, 16, 16, 24, 56, 1), (1, 16, 14, 14, 96, 216, 1), (1, 13, 23, 23, 48, 112, 1),

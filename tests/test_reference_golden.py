@@ -93,26 +93,29 @@ def test_oracle_matches_reference_model_py(path):
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype,tol,fuse", [("float32", 1e-4, "auto"), ("bfloat16", 2e-2, "auto"),
                                             ("bfloat16", 2e-2, "all"), ("bfloat16", 2e-2, "off"),
-                                            ("bfloat16", 2e-2, "v1")])
+                                            ("bfloat16", 2e-2, "v1"), ("bfloat16", 2e-2, "off+tma"),
+                                            ("bfloat16", 2e-2, "off+planar")])
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[4:-4] for p in CASES])
 def test_cuda_path_matches_reference_model_py(path, dtype, tol, fuse):
     """north_star tolerance: fp32 logits within 1e-4 relative, bf16 within 2e-2 relative with
     identical top-1 on EVERY fixture clip (relative = max |err| / max |logit|).  bf16 runs with the
     fused expand+channelwise kernel where the default rule places it ("auto"), on every layer that
-    has a tile plan ("all"), nowhere ("off") and with the round-1 fused kernel ("v1")."""
+    has a tile plan ("all"), nowhere ("off") and with the round-1 fused kernel ("v1"); "+tma" /
+    "+planar" pin the channelwise kernel (default "auto": planar on the wide stride-1 layers)."""
     from x3d_tf_b200 import model as M
     z, meta, cfg = _load(path)
     W = _weights(meta, cfg)
     M.reset_block_counters()
-    saved = M.Options.fuse_expand
-    M.Options.fuse_expand = fuse
+    saved = M.Options.fuse_expand, M.Options.channelwise
+    fuse, _, cw = fuse.partition("+")
+    M.Options.fuse_expand, M.Options.channelwise = fuse, cw or saved[1]
     try:
         m = M.X3D(cfg, dtype=dtype, use_cuda_graph=False)
         m.set_weights_dict(W)
         probs = m(torch.from_numpy(z["clips"]).cuda())
         torch.cuda.synchronize()
     finally:
-        M.Options.fuse_expand = saved
+        M.Options.fuse_expand, M.Options.channelwise = saved
     logits = m.last_logits.float().cpu().numpy()
     scale = np.abs(z["logits"]).max()
     err = np.abs(logits - z["logits"]).max() / scale

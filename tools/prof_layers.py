@@ -40,6 +40,13 @@ for si, (Hin, cin, inner, cout) in enumerate(stages):
             for se in (bool(a.se),):
                 timeit(f"dw s{si+2} {H}x{H}x{ci} stride{stride} se{int(se)}", lambda: ops.dw_fwd(x, w, b, stride, ph, ph, se),
                        (x.numel() + N * T * Ho * Ho * ci) * 2)
+        if a.what in ("dwp", "all") and ops.dw_planar_supported(T, H, H, ci, stride) > 0:
+            x = rnd(N, T, H, H, ci); w = rnd(27, ci, dtype=torch.float32); b = rnd(ci, dtype=torch.float32)
+            _, ph, _ = same_pad(H, 3, stride)
+            taps = ops.dw_planar_taps(w, b)
+            timeit(f"dwp s{si+2} {H}x{H}x{ci} stride{stride} se{a.se}", lambda: ops.dw_planar_fwd(x, taps, stride, ph, ph, bool(a.se)),
+                   (x.numel() + N * T * Ho * Ho * ci) * 2)
+            timeit(f"  (dw_tma)", lambda: ops.dw_fwd(x, w, b, stride, ph, ph, bool(a.se)), (x.numel() + N * T * Ho * Ho * ci) * 2)
         if a.what in ("ab", "ab2", "all"):
             cin_s = pad8(cin if stride == 2 else cout)
             x = rnd(N, T, H, H, cin_s); w = rnd(27, ci, dtype=torch.float32); b = rnd(ci, dtype=torch.float32)

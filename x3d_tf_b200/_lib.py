@@ -58,6 +58,9 @@ SIGNATURES = {
     "x3d_dw3x3x3_act_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "x3d_dw_planar_partial_blocks": (C.c_int, [C.c_int] * 5),
+    "x3d_dw_planar_lane_permille": (C.c_int, [C.c_int] * 5),
+    "x3d_dw3x3x3_planar_fwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 9 + [C.c_void_p]),
     "x3d_se_mlp_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p]),

@@ -296,6 +296,12 @@ class Options:
     # is the FMA/issue-bound kernel), step 11.91 -> 11.75 ms (+1.4 % clips/s); X3D_SWISH_IN_DW=0 turns
     # it off.
     swish_in_dw = os.environ.get("X3D_SWISH_IN_DW", "1") == "1"
+    # channelwise 3x3x3 kernel for bf16 activations: "tma" = x3d_dw3x3x3_act_fwd (thread = channel pair,
+    # csrc/x3d_dw_tma.cu) everywhere; "auto" = the planar kernel (lanes = pixels, taps in uniform
+    # registers, csrc/x3d_dw_planar.cu) for the stride-1 layers wider than 8 pixels that fill >= 90 % of
+    # its lane grid (all of them at 256^2, none at 224^2 / 182^2), where it measures 5-13 % faster
+    # (profiles/r02_dw_planar.md); "planar" = wherever it has a plan.
+    channelwise = os.environ.get("X3D_CHANNELWISE", "auto")
     # pointwise convs whose rows are not a multiple of 32 bytes (24 / 56 channels): two pixels per GEMM
     # row with a block-diagonal weight (PointwiseConv).  Measured at 80 clips of 16x256^2 (step, a,
     # shortcut in ms): off 11.66 / 2.95 / 0.52; factor 2 10.97 / 2.47 / 0.37; factor 4 11.07; factor 2
@@ -442,6 +448,7 @@ class Bottleneck(Layer):
             wb = self._vars["b/kernel"].reshape(27, self.inner).astype(np.float64) * sb
             d["wb"] = _dev_f32(_pad_to(wb, 1, ci), device)
             d["bb"] = _dev_f32(_pad_to(tb, 0, ci), device)
+            d["wbp"] = ops.dw_planar_taps(d["wb"], d["bb"])
             if self.has_se:
                 w1 = self._vars["se_fc1/kernel"].reshape(self.inner, self.se_width)
                 w2 = self._vars["se_fc2/kernel"].reshape(self.se_width, self.inner)
@@ -484,7 +491,15 @@ class Bottleneck(Layer):
             # blocks without SE: the swish that follows bn_b goes into the stencil's epilogue, so the
             # projection GEMM runs without its transform warps (its fastest form)
             swish_in_b = Options.swish_in_dw and not self.has_se
-            b, partial = ops.dw_fwd(a, d["wb"], d["bb"], self.stride, ph, pw, self.has_se, swish=swish_in_b)
+            cw = Options.channelwise
+            planar = a.dtype == torch.bfloat16 and cw != "tma" and \
+                ops.dw_planar_supported(T, H, W, ci, self.stride) > 0 and \
+                (cw == "planar" or (self.stride == 1 and W > 8 and
+                                    ops.dw_planar_lane_use(T, H, W, ci, self.stride) >= 0.9))
+            if planar:
+                b, partial = ops.dw_planar_fwd(a, d["wbp"], self.stride, ph, pw, self.has_se, swish=swish_in_b)
+            else:
+                b, partial = ops.dw_fwd(a, d["wb"], d["bb"], self.stride, ph, pw, self.has_se, swish=swish_in_b)
             del a
         _, _, Ho, Wo, _ = b.shape
         se = None
@@ -757,7 +772,7 @@ class X3D(Layer):
         over their own input/output buffers that share slot 0's memory pool (replays are
         stream-ordered), used by `predict` to overlap the H2D copy of the next batch."""
         key = (tuple(shape), dtype, str(device), Options.pointwise, Options.stem, Options.stem_u8, Options.swish_in_dw,
-               Options.fuse_expand, slot)
+               Options.fuse_expand, Options.channelwise, slot)
         if key not in self._graphs:
             static_in = torch.zeros(tuple(shape), dtype=dtype, device=device)
             self._forward(static_in, training)

@@ -257,6 +257,50 @@ def dw_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: int, pa
     return out, partial
 
 
+def dw_planar_taps(w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """[27, C] BN-folded taps + [C] shift -> the planar kernel's table [C/2, 28, 2] (fp32, device)."""
+    C = w.shape[1]
+    t = torch.cat([w, bias.view(1, C)], 0)                       # [28, C]
+    return t.view(28, C // 2, 2).permute(1, 0, 2).contiguous()
+
+
+def dw_planar_supported(T: int, H: int, W: int, c: int, stride: int) -> int:
+    """SE partial blocks per clip of the planar channelwise kernel, 0 if it does not take the shape."""
+    if c % 8 or c // 2 > 288:
+        return 0
+    return int(lib().x3d_dw_planar_partial_blocks(T, H, W, c, stride))
+
+
+def dw_planar_lane_use(T: int, H: int, W: int, c: int, stride: int) -> float:
+    """Fraction of the planar kernel's lane grid that a shape fills (1.0: no padding lanes); 0 without a plan."""
+    if c % 8 or c // 2 > 288:
+        return 0.0
+    return int(lib().x3d_dw_planar_lane_permille(T, H, W, c, stride)) / 1000.0
+
+
+def dw_planar_fwd(x: torch.Tensor, taps: torch.Tensor, stride: int, pad_h: int, pad_w: int, want_se: bool,
+                  swish: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Channelwise 3x3x3 + BN (+ swish | SE sums), lanes = pixels / uniform-register taps (bf16)."""
+    _req(x, "x")
+    if x.dtype != torch.bfloat16:
+        raise TypeError("dw_planar_fwd needs bf16 activations")
+    if swish and want_se:
+        raise ValueError("swish in the epilogue only without SE (the SE scale comes before the swish)")
+    N, T, H, W, C = x.shape
+    Ho, Wo = -(-H // stride), -(-W // stride)
+    out = torch.empty((N, T, Ho, Wo, C), dtype=x.dtype, device=x.device)
+    partial = None
+    if want_se:
+        nblk = dw_planar_supported(T, H, W, C, stride)
+        if nblk <= 0:
+            raise _lib.X3DLibError("x3d_dw_planar_partial_blocks rejected the shape")
+        partial = torch.empty((N, nblk, C), dtype=torch.float32, device=x.device)
+    _launch("x3d_dw3x3x3_planar_fwd", lambda: lib().x3d_dw3x3x3_planar_fwd(
+        x.data_ptr(), taps.data_ptr(), out.data_ptr(), _ptr(partial), N, T, H, W, C, stride, pad_h, pad_w,
+        1 if swish else 0, _stream()))
+    return out, partial
+
+
 def expand_dw_supported(T: int, H: int, W: int, cin: int, c: int, stride: int) -> int:
     """Number of SE partial blocks of the fused kernel's launch, 0 if no tile plan fits."""
     return int(lib().x3d_expand_dw_partial_blocks(T, H, W, cin, c, stride))
