@@ -179,14 +179,26 @@ int x3d_head_fc_fwd(const float* A, const float* Wt, const float* bias, float* D
  * Same contract as x3d_pw_fwd for a_dtype = d_dtype = X3D_BF16 and gather == 0, but the weights
  * are pre-packed bf16: Wp [Npad, Kpad] (K contiguous), Npad % 16 == 0, Kpad % 64 == 0, zero
  * padded, BN scale folded.  A tiles arrive by TMA (128B swizzle), tcgen05.mma accumulates in
- * TMEM, the epilogue adds bias (+ residual), applies ReLU and stores bf16. */
+ * TMEM, the epilogue adds bias (+ residual), applies ReLU and stores bf16.
+ *
+ * Second source (A2 != NULL; ResBlock's shortcut conv + bn_r folded into the projection conv,
+ * model.py:360-367,386-392):  D = act(bias + pro(A) . W[0:K] + A2s . W[K1:K1+K2]) with
+ *   A2   [a2_nt, a2_hi, a2_wi, K2] bf16 NDHWC block input (frames flattened), A2s[m] = A2[nt, s*ho, s*wo]
+ *        for output pixel m = (nt*Ho + ho)*Wo + wo, Ho=(a2_hi-1)/s+1, Wo=(a2_wi-1)/s+1, s = a2_stride
+ *        (the 'valid' stride-(1,s,s) 1x1x1 conv of the reference); M must equal a2_nt*Ho*Wo;
+ *   Wp   holds the second source's K2 rows at packed column K1 = 64*ceil(K/64) (Kpad >= K1 + 64*ceil(K2/64));
+ *   the prologue (se / swish) applies to the first source only; R must be NULL; bias = sum of both shifts.
+ * Needs 128-pixel tiles that are whole rows of a frame or whole frames: x3d_pw_tc_sampler_supported
+ * (1 / 0); otherwise gather with x3d_gather_rows_fwd and pass the shortcut's result as R. */
 typedef struct x3d_pw_tc_args {
   const void* A; const void* Wp; const float* bias; const void* R; const float* se; void* D;
   int64_t M; int32_t K, Nc, lda, ldr, ldd, Kpad, Npad;
   int64_t rows_per_clip;
   int32_t swish, relu;
+  const void* A2; int64_t a2_nt; int32_t K2, a2_stride, a2_hi, a2_wi;
 } x3d_pw_tc_args;
 int x3d_pw_tc_fwd(const x3d_pw_tc_args* args, void* stream);
+int x3d_pw_tc_sampler_supported(int Hi, int Wi, int stride);
 
 /* ---- Fused expand + channelwise: Bottleneck.a + bn_a + ReLU + b + bn_b (+ se_pool sums), ----
  * ---- model.py:306-312, as one kernel (bf16 storage) ------------------------------------------

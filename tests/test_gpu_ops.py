@@ -324,6 +324,41 @@ def test_pointwise_tcgen05_prologue_epilogue():
         assert rel_err(to_np(got2), _pw_ref(a, w, bias, swish=True)) < 1.2e-2
 
 
+@pytest.mark.parametrize("NT,Hi,Wi,K,K2,N,stride,pro", [
+    (6, 32, 32, 112, 24, 48, 2, False),      # 16x16 frames: half a frame per tile
+    (8, 16, 16, 216, 48, 96, 2, True),       # 8x8 frames: two frames per tile
+    (5, 16, 16, 432, 96, 192, 2, False),     # odd frame count: last tile half outside the tensor
+    (3, 127, 128, 56, 24, 24, 2, True),      # odd height: Ho = 64, last sampled row is 126
+    (2, 64, 64, 56, 24, 24, 1, True),        # stride 1 (channel change only)
+])
+def test_pointwise_tcgen05_shortcut_as_extra_k(NT, Hi, Wi, K, K2, N, stride, pro):
+    """x3d_pw_tc_fwd's second source: relu(bias + pro(A).W + sample(X).W2) against the fp64 formula."""
+    rng = np.random.default_rng(NT * Hi + K)
+    ops = _ops()
+    assert ops.pw_tc_sampler_supported(Hi, Wi, stride)
+    Ho, Wo = (Hi - 1) // stride + 1, (Wi - 1) // stride + 1
+    M = NT * Ho * Wo
+    a = bf16_round(rng.normal(size=(M, K)))
+    x = bf16_round(rng.normal(size=(1, NT, Hi, Wi, K2)))
+    w = bf16_round(rng.normal(size=(K, N)) / np.sqrt(K))
+    w2 = bf16_round(rng.normal(size=(K2, N)) / np.sqrt(K2))
+    bias = rng.normal(size=N).astype(np.float32)
+    k1 = (K + 63) // 64 * 64
+    wp = np.zeros(((N + 15) // 16 * 16, k1 + (K2 + 63) // 64 * 64), np.float32)
+    wp[:N, :K] = w.T
+    wp[:N, k1:k1 + K2] = w2.T
+    rpc = 2 * Ho * Wo                                           # two frames per "clip"
+    se = rng.uniform(0.1, 0.9, size=(-(-M // rpc), K)).astype(np.float32) if pro else None
+    got = ops.pw_tc_fwd(to_dev(a, torch.bfloat16), to_dev(wp, torch.bfloat16), to_dev(bias), M=M, K=K, Nc=N,
+                        se=to_dev(se) if pro else None, rows_per_clip=rpc if pro else 0, swish=pro, relu=True,
+                        a2=to_dev(x, torch.bfloat16), a2_stride=stride)
+    torch.cuda.synchronize()
+    xs = x[0, :, ::stride, ::stride, :].reshape(M, K2).astype(np.float64)
+    want = _pw_ref(a, w, bias, xs @ w2.astype(np.float64), se, rpc, pro, True)
+    assert rel_err(to_np(got), want) < (1.2e-2 if pro else 2.0 ** -7), (NT, Hi, Wi)
+    assert not ops.pw_tc_sampler_supported(112, 112, 2) and not ops.pw_tc_sampler_supported(91, 91, 2)
+
+
 def test_pointwise_tcgen05_matches_simt_bitwise_inputs():
     """Same bf16 inputs through both pointwise kernels: results agree to bf16 rounding."""
     rng = np.random.default_rng(3)

@@ -35,7 +35,9 @@ class PwTcArgs(C.Structure):
                 ("se", C.c_void_p), ("D", C.c_void_p),
                 ("M", C.c_int64), ("K", C.c_int32), ("Nc", C.c_int32), ("lda", C.c_int32),
                 ("ldr", C.c_int32), ("ldd", C.c_int32), ("Kpad", C.c_int32), ("Npad", C.c_int32),
-                ("rows_per_clip", C.c_int64), ("swish", C.c_int32), ("relu", C.c_int32)]
+                ("rows_per_clip", C.c_int64), ("swish", C.c_int32), ("relu", C.c_int32),
+                ("A2", C.c_void_p), ("a2_nt", C.c_int64), ("K2", C.c_int32), ("a2_stride", C.c_int32),
+                ("a2_hi", C.c_int32), ("a2_wi", C.c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol include/x3d_b200.h declares.
@@ -69,6 +71,7 @@ SIGNATURES = {
     "x3d_softmax_viewmean_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p]),
     "x3d_pw_tc_fwd": (C.c_int, [C.POINTER(PwTcArgs), C.c_void_p]),
+    "x3d_pw_tc_sampler_supported": (C.c_int, [C.c_int] * 3),
     "x3d_gather_rows_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_void_p]),
     "x3d_expand_dw_partial_blocks": (C.c_int, [C.c_int] * 6),

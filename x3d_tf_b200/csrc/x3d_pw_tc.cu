@@ -11,7 +11,11 @@
 //   * 2 groups of 4 epilogue warps (one per TMEM accumulator) read TMEM with tcgen05.ld, add bias
 //     (+ residual, prefetched), ReLU, pack bf16 into swizzled staging and TMA-store full lines;
 //   * optional prologue (projection conv, model.py:311-317): 8 transform warps apply
-//     swish(se[clip,k] * a) in place on each landed stage before the MMA consumes it.
+//     swish(se[clip,k] * a) in place on each landed stage before the MMA consumes it;
+//   * optional second A source (ResBlock's strided shortcut conv + bn_r, model.py:360-367,386-389):
+//     the K loop continues over the block INPUT, read through a 4-D tensor map whose strides pick
+//     the pixels (t, s*ho, s*wo), against the shortcut's weights stacked under the projection's:
+//     D = bn_c(c(h)) + bn_r(r(x)) in one fp32 accumulator, no gather kernel, no residual tensor.
 //
 // Reference call sites replaced: Bottleneck.a/bn_a/relu (model.py:306-308), Bottleneck.c/bn_c +
 // ResBlock add/relu (model.py:317-318,389-392), conv5 (model.py:117).
@@ -94,8 +98,12 @@ struct Params {
   int Nc;          // stored output channels (multiple of 8)
   int ldr, ldd;
   int NT;          // N tile of this launch (multiple of 16, <= 256)
-  int KC;          // number of 64-wide K chunks
-  int k16_last;    // number of K=16 MMAs in the last chunk (1..4)
+  int KC;          // number of 64-wide K chunks (both sources)
+  int k16_last;    // number of K=16 MMAs in the last chunk of the LAST source (1..4)
+  int KC1;         // chunks of the first source (== KC without a second source)
+  int k16_last1;   // K=16 MMAs in the last chunk of the first source
+  int a2_ppf;      // second source: output pixels per frame (Ho*Wo), 0 without one
+  int a2_wo;       // second source: output row length
   int stages;      // A ring depth
   int tmem_cols;   // power of two >= 2*NT
   int relu, swish;
@@ -107,7 +115,8 @@ constexpr int kThreadsPlain = 64 + 32 * kEpiWarps, kThreadsPro = kThreadsPlain +
 template <bool kPro>
 __global__ void __launch_bounds__(kPro ? kThreadsPro : kThreadsPlain, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-             const __grid_constant__ CUtensorMap tmD, const Params p) {
+             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmA2,
+             const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -136,6 +145,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
     prefetch_tmap(&tmD);
+    if (p.a2_ppf) prefetch_tmap(&tmA2);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -172,10 +182,17 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t ph = 0;
       for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = static_cast<int>(tile * kBlockM);
+        // second source: the tile's 128 output pixels are whole rows of one frame (or whole frames)
+        int nt0 = 0, ho0 = 0;
+        if (p.a2_ppf) {
+          nt0 = row0 / p.a2_ppf;
+          ho0 = (row0 - nt0 * p.a2_ppf) / p.a2_wo;
+        }
         for (int kc = 0; kc < p.KC; ++kc) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], kStageBytes);
-          tma_load_2d(sA + s * kStageBytes, &tmA, kc * kBlockK, row0, &full[s]);
+          if (kc < p.KC1) tma_load_2d(sA + s * kStageBytes, &tmA, kc * kBlockK, row0, &full[s]);
+          else tma_load_4d(smem_u32(sA + s * kStageBytes), &tmA2, (kc - p.KC1) * kBlockK, 0, ho0, nt0, &full[s]);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -199,7 +216,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(sA + s * kStageBytes);
           const uint32_t b_addr = smem_u32(sW + kc * w_chunk_bytes);
-          const int nk = (kc == p.KC - 1) ? p.k16_last : 4;
+          const int nk = (kc == p.KC - 1) ? p.k16_last : (kc == p.KC1 - 1 ? p.k16_last1 : 4);
           for (int k = 0; k < nk; ++k)
             umma_bf16(d_tmem, make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32),
                       idesc, (kc | k) != 0 ? 1u : 0u);
@@ -355,7 +372,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool one_clip = rem0 + kBlockM <= rpc;            // whole tile inside one clip
       for (int kc = 0; kc < p.KC; ++kc) {
         const int k = kc * kBlockK + kin;
-        const bool k_ok = k < p.Kc;                           // beyond Kc the stage holds TMA zeros
+        // beyond Kc the stage holds TMA zeros; chunks of the second source are not transformed
+        const bool k_ok = k < p.Kc && kc < p.KC1;
         float2 sc[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) sc[j] = make_float2(1.f, 1.f);
@@ -443,11 +461,42 @@ static bool make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Strided pixel sampler of the shortcut conv: [C, Wo, Ho, NT] over an NDHWC tensor [NT, Hi, Wi, C]
+// with element (c, wo, ho, nt) = in[nt, s*ho, s*wo, c]; box = 64 channels x 128 output pixels.
+static bool make_map_sampler(CUtensorMap* m, const void* base, int C, int Hi, int Wi, long NT, int s,
+                             int bw, int bh, int bf) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  const int Ho = (Hi - 1) / s + 1, Wo = (Wi - 1) / s + 1;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)NT};
+  cuuint64_t strides[3] = {(cuuint64_t)s * C * 2, (cuuint64_t)s * Wi * C * 2, (cuuint64_t)Hi * Wi * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bf};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// 128 consecutive output pixels must be whole rows of one frame, or whole frames
+static bool sampler_box(int Ho, int Wo, int* bh, int* bf) {
+  if (Wo <= 0 || Wo > kBlockM || kBlockM % Wo) return false;
+  const int rh = kBlockM / Wo;
+  if (rh <= Ho) { if (Ho % rh) return false; *bh = rh; *bf = 1; return true; }
+  if (rh % Ho) return false;
+  *bh = Ho; *bf = rh / Ho;
+  return true;
+}
 
 }  // namespace tc
 }  // namespace x3d
 
 using namespace x3d;
+
+extern "C" int x3d_pw_tc_sampler_supported(int Hi, int Wi, int stride) {
+  if (Hi <= 0 || Wi <= 0 || stride < 1) return 0;
+  int bh, bf;
+  return tc::sampler_box((Hi - 1) / stride + 1, (Wi - 1) / stride + 1, &bh, &bf) ? 1 : 0;
+}
 
 extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   X3D_REQUIRE(a && a->A && a->Wp && a->D, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: null pointer");
@@ -463,11 +512,25 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
               (reinterpret_cast<uintptr_t>(a->D) & 15) == 0, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: pointers must be 16-byte aligned");
   X3D_REQUIRE(device_sm_count() > 0 && device_is_sm100(), X3D_ERR_NO_DEVICE, "x3d_pw_tc_fwd: needs an sm_100 device");
   // N tiling: fewest tiles with NT <= 256 whose resident weight slice leaves >= 3 A stages.
-  const int kc_n = a->Kpad / 64;
   const int k16_total = (a->K + 15) / 16;
-  const int KC = (k16_total + 3) / 4;                 // chunks that actually hold data
-  const int k16_last = k16_total - (KC - 1) * 4;
-  (void)kc_n;
+  const int KC1 = (k16_total + 3) / 4;                // chunks that actually hold data
+  const int k16_last1 = k16_total - (KC1 - 1) * 4;
+  int KC = KC1, k16_last = k16_last1, a2_bh = 0, a2_bf = 0, a2_ho = 0, a2_wo = 0;
+  if (a->A2) {
+    // second source: its K2 channels continue the K loop at column KC1*64 of the packed weight
+    X3D_REQUIRE(!a->R, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: A2 (shortcut as extra K) and R (residual) exclude each other");
+    X3D_REQUIRE(a->K2 > 0 && a->K2 % 8 == 0 && a->a2_stride >= 1 && a->a2_hi > 0 && a->a2_wi > 0 && a->a2_nt > 0,
+                X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: bad second source K2=%d stride=%d %dx%d", a->K2, a->a2_stride, a->a2_hi, a->a2_wi);
+    X3D_REQUIRE((reinterpret_cast<uintptr_t>(a->A2) & 15) == 0, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: A2 must be 16-byte aligned");
+    a2_ho = (a->a2_hi - 1) / a->a2_stride + 1; a2_wo = (a->a2_wi - 1) / a->a2_stride + 1;
+    X3D_REQUIRE(a->M == a->a2_nt * a2_ho * a2_wo, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: M=%ld is not nt*Ho*Wo = %ld*%d*%d",
+                (long)a->M, (long)a->a2_nt, a2_ho, a2_wo);
+    X3D_REQUIRE(tc::sampler_box(a2_ho, a2_wo, &a2_bh, &a2_bf), X3D_ERR_UNSUPPORTED,
+                "x3d_pw_tc_fwd: 128-pixel tiles do not align with %dx%d frames (x3d_pw_tc_sampler_supported)", a2_ho, a2_wo);
+    const int k16_2 = (a->K2 + 15) / 16, KC2 = (k16_2 + 3) / 4;
+    KC = KC1 + KC2; k16_last = k16_2 - (KC2 - 1) * 4;
+    X3D_REQUIRE(a->Kpad >= KC * 64, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: Kpad=%d < %d (both sources, 64-wide chunks)", a->Kpad, KC * 64);
+  }
   const int budget = device_max_smem() - 1024 /*align*/ - 1024 /*bias*/ - 512 /*barriers*/ -
                      tc::kOutBufs * tc::kStageBytes /*output staging*/;
   // The epilogue stores 64-column boxes, so with more than one N tile the tile width must be a
@@ -499,9 +562,14 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   CUtensorMap tmD;
   X3D_REQUIRE(tc::make_map_2d(&tmD, a->D, (uint64_t)a->Nc, (uint64_t)a->M, (uint64_t)a->ldd * 2, 64, 128),
               X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: tensor map for D failed (Nc=%d M=%ld ldd=%d)", a->Nc, (long)a->M, a->ldd);
+  CUtensorMap tmA2 = tmA;
+  if (a->A2)
+    X3D_REQUIRE(tc::make_map_sampler(&tmA2, a->A2, a->K2, a->a2_hi, a->a2_wi, (long)a->a2_nt, a->a2_stride, a2_wo, a2_bh, a2_bf),
+                X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: tensor map for A2 failed (K2=%d %dx%d stride %d)", a->K2, a->a2_hi, a->a2_wi, a->a2_stride);
   tc::Params p;
   p.bias = a->bias; p.R = static_cast<const bf16*>(a->R); p.se = a->se; p.D = static_cast<bf16*>(a->D);
   p.M = a->M; p.rows_per_clip = a->rows_per_clip; p.Kc = a->K; p.Nc = a->Nc; p.ldr = a->ldr; p.ldd = a->ldd;
+  p.KC1 = KC1; p.k16_last1 = k16_last1; p.a2_ppf = a->A2 ? a2_ho * a2_wo : 0; p.a2_wo = a2_wo;
   p.NT = NT; p.KC = KC; p.k16_last = k16_last; p.stages = stages; p.tmem_cols = tmem_cols;
   p.relu = a->relu; p.swish = a->swish;
 
@@ -518,11 +586,11 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   if (pro) {
     e = ensure_dynamic_smem(tc::pw_tc_kernel<true>, optin_pro, smem, false);
     X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
-    tc::pw_tc_kernel<true><<<grid, tc::kThreadsPro, smem, st>>>(tmA, tmW, tmD, p);
+    tc::pw_tc_kernel<true><<<grid, tc::kThreadsPro, smem, st>>>(tmA, tmW, tmD, tmA2, p);
   } else {
     e = ensure_dynamic_smem(tc::pw_tc_kernel<false>, optin_plain, smem, false);
     X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
-    tc::pw_tc_kernel<false><<<grid, tc::kThreadsPlain, smem, st>>>(tmA, tmW, tmD, p);
+    tc::pw_tc_kernel<false><<<grid, tc::kThreadsPlain, smem, st>>>(tmA, tmW, tmD, tmA2, p);
   }
   return check_launch("x3d_pw_tc_fwd");
 }

@@ -220,6 +220,7 @@ class PointwiseConv:
             torch.bfloat16).contiguous()
         self._k2t = _pad_to(_pad_to(k2.T, 0, self.Ns), 1, self.Ks)               # [Ns, Ks], fp64
         self._paired: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._stacked: Dict[int, tuple] = {}
 
     # Pixel pairing (Options.pair_pixels): rows of 24 or 56 bf16 channels are 48 / 112 bytes and straddle
     # 32-byte sectors, so TMA moves 1.33x / 1.14x the useful bytes between L2 and shared memory, and a
@@ -252,6 +253,30 @@ class PointwiseConv:
                 torch.bfloat16).contiguous()
             self._paired[P] = (wp, self.bias.repeat(P).contiguous())
         return self._paired[P]
+
+    def _stacked_weights(self, other: "PointwiseConv", device) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Packed weight of  self(a) + other(a2)  as ONE GEMM over [a | a2]: other's K rows start at the
+        packed column 64*ceil(Ks/64) (x3d_pw_tc_fwd's second source); the two BN shifts add up."""
+        key = id(other)
+        if key not in self._stacked:
+            if other.Ns != self.Ns:
+                raise ValueError("stacked pointwise convs need the same output width")
+            k1, k2 = (self.Ks + 63) // 64 * 64, (other.Ks + 63) // 64 * 64
+            w = np.zeros(((self.Ns + 15) // 16 * 16, k1 + k2), np.float64)
+            w[:self.Ns, :self.Ks] = self._k2t
+            w[:self.Ns, k1:k1 + other.Ks] = other._k2t
+            wp = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)).to(device).to(
+                torch.bfloat16).contiguous()
+            self._stacked[key] = (wp, (self.bias + other.bias).contiguous(), other)
+        return self._stacked[key][:2]
+
+    def run_with_shortcut(self, a: torch.Tensor, M: int, shortcut: "PointwiseConv", x: torch.Tensor,
+                          stride: int, *, se=None, rows_per_clip=0, swish=False, relu=False) -> torch.Tensor:
+        """act(self(pro(a)) + shortcut(x sampled with `stride`)): ResBlock's add with the shortcut conv as
+        extra K columns of the projection GEMM (reference model.py:386-392)."""
+        wp, bias = self._stacked_weights(shortcut, a.device)
+        return ops.pw_tc_fwd(a, wp, bias, M=M, K=self.Ks, Nc=self.Ns, se=se, rows_per_clip=rows_per_clip,
+                             swish=swish, relu=relu, a2=x, a2_stride=stride)
 
     def run(self, a: torch.Tensor, M: int, *, use_tc: bool, out_dtype=None, residual=None,
             se=None, rows_per_clip=0, swish=False, relu=False, gather=None, pair_rows=0) -> torch.Tensor:
@@ -296,6 +321,10 @@ class Options:
     # is the FMA/issue-bound kernel), step 11.91 -> 11.75 ms (+1.4 % clips/s); X3D_SWISH_IN_DW=0 turns
     # it off.
     swish_in_dw = os.environ.get("X3D_SWISH_IN_DW", "1") == "1"
+    # bf16 + "tc": ResBlock's strided shortcut conv + bn_r as extra K columns of the projection GEMM
+    # (x3d_pw_tc_fwd's second source: no gather kernel, no shortcut GEMM, no residual tensor) wherever
+    # 128-pixel tiles align with the output frames (64/32/16/8-wide: every stage at 256^2).
+    fold_shortcut = os.environ.get("X3D_FOLD_SHORTCUT", "1") == "1"
     # channelwise 3x3x3 kernel for bf16 activations: "tma" = x3d_dw3x3x3_act_fwd (thread = channel pair,
     # csrc/x3d_dw_tma.cu) everywhere; "auto" = the planar kernel (lanes = pixels, taps in uniform
     # registers, csrc/x3d_dw_planar.cu) for the stride-1 layers wider than 8 pixels that fill >= 90 % of
@@ -460,8 +489,9 @@ class Bottleneck(Layer):
         return self._dev[key]
 
     def _forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None,
-                 relu: bool = False) -> torch.Tensor:
-        """x: [N,T,H,W,pad8(cin)].  `residual`/`relu`: the ResBlock add + ReLU fused into c's epilogue."""
+                 relu: bool = False, shortcut: Optional[PointwiseConv] = None) -> torch.Tensor:
+        """x: [N,T,H,W,pad8(cin)].  `residual`/`relu`: the ResBlock add + ReLU fused into c's epilogue;
+        `shortcut`: ResBlock's strided conv + bn_r, run on x as extra K columns of c (then no `residual`)."""
         if self.in_channels is None:
             raise RuntimeError("Bottleneck used before its input width is known")
         d = self._prep(x.device)
@@ -507,8 +537,12 @@ class Bottleneck(Layer):
             ops.Profiler.tag = "se"
             se = ops.se_mlp_fwd(partial, T * Ho * Wo, d["w1"], d["b1"], d["w2"], d["b2"])
         ops.Profiler.tag = "c"
-        out = d["c"].run(b, N * T * Ho * Wo, use_tc=tc, se=se, rows_per_clip=T * Ho * Wo,
-                         swish=not swish_in_b, residual=residual, relu=relu)
+        if shortcut is not None:
+            out = d["c"].run_with_shortcut(b, N * T * Ho * Wo, shortcut, x, self.stride, se=se,
+                                           rows_per_clip=T * Ho * Wo, swish=not swish_in_b, relu=relu)
+        else:
+            out = d["c"].run(b, N * T * Ho * Wo, use_tc=tc, se=se, rows_per_clip=T * Ho * Wo,
+                             swish=not swish_in_b, residual=residual, relu=relu)
         return out.view(N, T, Ho, Wo, _pad8(self.out_channels))
 
     def call(self, input, training: bool = False):
@@ -559,6 +593,9 @@ class ResBlock(Layer):
             s = self.stride
             Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
             ops.Profiler.tag = "shortcut"
+            if _use_tc() and x.dtype == torch.bfloat16 and Options.fold_shortcut and \
+                    ops.pw_tc_sampler_supported(H, W, s):
+                return self.bottleneck._forward(x, relu=True, shortcut=d["r"])
             if _use_tc() and x.dtype == torch.bfloat16:
                 # sampled pixels -> dense matrix -> tensor-core GEMM (bn_r folded)
                 rows = x.view(-1, x.shape[-1]) if s == 1 else ops.gather_rows_fwd(x, s)
@@ -772,7 +809,7 @@ class X3D(Layer):
         over their own input/output buffers that share slot 0's memory pool (replays are
         stream-ordered), used by `predict` to overlap the H2D copy of the next batch."""
         key = (tuple(shape), dtype, str(device), Options.pointwise, Options.stem, Options.stem_u8, Options.swish_in_dw,
-               Options.fuse_expand, Options.channelwise, slot)
+               Options.fuse_expand, Options.channelwise, Options.fold_shortcut, slot)
         if key not in self._graphs:
             static_in = torch.zeros(tuple(shape), dtype=dtype, device=device)
             self._forward(static_in, training)

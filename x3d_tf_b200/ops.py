@@ -192,8 +192,9 @@ def pw_fwd(a: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, M
 def pw_tc_fwd(a: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], *, M: int, K: int,
               Nc: int, out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
               se: Optional[torch.Tensor] = None, rows_per_clip: int = 0, swish: bool = False,
-              relu: bool = False) -> torch.Tensor:
-    """tcgen05 pointwise GEMM (bf16).  `wp` is the packed [Npad, Kpad] bf16 weight."""
+              relu: bool = False, a2: Optional[torch.Tensor] = None, a2_stride: int = 1) -> torch.Tensor:
+    """tcgen05 pointwise GEMM (bf16).  `wp` is the packed [Npad, Kpad] bf16 weight.
+    `a2` [N,T,Hi,Wi,K2]: second K source sampled at (t, s*ho, s*wo) -- the shortcut conv folded in."""
     _req(a, "a")
     if a.dtype != torch.bfloat16:
         raise TypeError("pw_tc_fwd needs bf16 activations")
@@ -207,8 +208,19 @@ def pw_tc_fwd(a: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], *
     args.Npad, args.Kpad = wp.shape
     args.rows_per_clip = rows_per_clip
     args.swish, args.relu = int(swish), int(relu)
+    if a2 is not None:
+        _req(a2, "a2")
+        if a2.dtype != torch.bfloat16 or a2.dim() != 5:
+            raise TypeError("pw_tc_fwd: a2 must be a bf16 [N,T,H,W,C] tensor")
+        args.A2, args.a2_nt, args.K2 = a2.data_ptr(), a2.shape[0] * a2.shape[1], a2.shape[4]
+        args.a2_stride, args.a2_hi, args.a2_wi = a2_stride, a2.shape[2], a2.shape[3]
     _launch("x3d_pw_tc_fwd", lambda: lib().x3d_pw_tc_fwd(args, _stream()))
     return out
+
+
+def pw_tc_sampler_supported(Hi: int, Wi: int, stride: int) -> bool:
+    """Can x3d_pw_tc_fwd read a stride-`stride` pixel sample of Hi x Wi frames as its second source?"""
+    return bool(lib().x3d_pw_tc_sampler_supported(Hi, Wi, stride))
 
 
 def gather_rows_fwd(x: torch.Tensor, stride: int) -> torch.Tensor:
