@@ -435,7 +435,7 @@ def test_gather_rows_is_bit_exact(dtype, H, W, stride, C):
 
 
 @pytest.mark.parametrize("M,K,N,relu", [(80, 432, 2048, True), (80, 2048, 400, False), (1, 432, 2048, True),
-                                        (7, 64, 20, False), (130, 72, 36, True)])
+                                        (7, 64, 20, False), (130, 72, 36, True), (300, 2200, 52, False)])
 def test_head_fc(M, K, N, relu):
     rng = np.random.default_rng(M + K + N)
     a = rng.normal(size=(M, K)).astype(np.float32)

@@ -540,35 +540,56 @@ gather_rows_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long r
 // work is streaming the fp32 weights once.  CTA = 16 output columns x up to 128 rows; K is walked
 // in chunks of 64 staged in shared memory; thread = (column, row group of 8).
 constexpr int kSkK = 64, kSkM = 128;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cluster_rank(uint32_t smem_addr, int rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float ld_cluster_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 
-// SKN output columns per CTA (16, or 4 when 16 would leave most SMs idle: fc2 has 400 columns and
-// K = 2048, i.e. 25 CTAs each walking 32 K chunks one after the other with the 16-column tile).
+// Small-M GEMM of the head (M = clips in flight, <= a few hundred rows): latency-bound, so the K range
+// is split over the CTAs of a thread-block cluster (cluster dim z = splits), every CTA walks only
+// K/splits (4 chunks of 64 at fc2's K = 2048 with 8 splits instead of 32 one after the other) and
+// reads only its K slice of A; the partial tiles meet in the first CTA's epilogue through distributed
+// shared memory, summed in rank order (deterministic).  SKN output columns per CTA (16, or 4 when 16
+// would leave most SMs idle).
 template <int SKN>
 __global__ void __launch_bounds__(256)
 skinny_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
                    const float* __restrict__ bias, float* __restrict__ D, int M, int K, int Nc,
-                   int lda, int ldw, int ldd, int relu) {
+                   int lda, int ldw, int ldd, int relu, int k_per) {
   constexpr int kGroups = 256 / SKN, kRows = kSkM / kGroups;     // row groups, rows per thread
   __shared__ __align__(16) float As[kSkM][kSkK + 4];
   __shared__ __align__(16) float Ws[kSkK][SKN];
+  __shared__ __align__(16) float Part[kSkM][SKN];                // this CTA's partial tile (read by rank 0)
   const int tid = threadIdx.x, c = tid % SKN, g = tid / SKN;
   const int n0 = blockIdx.x * SKN, m0 = blockIdx.y * kSkM;
   const int rows = min(kSkM, M - m0);
+  const int splits = gridDim.z, kz = blockIdx.z;                 // cluster = the splits of one tile
+  const int k_lo = kz * k_per, k_hi = min(K, k_lo + k_per);
   float acc[kRows];
 #pragma unroll
   for (int i = 0; i < kRows; ++i) acc[i] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += kSkK) {
+  for (int k0 = k_lo; k0 < k_hi; k0 += kSkK) {
     __syncthreads();
     for (int i = tid; i < kSkM * (kSkK / 4); i += 256) {
       const int r = i / (kSkK / 4), kv = (i - r * (kSkK / 4)) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < rows && k0 + kv < K) v = __ldg(reinterpret_cast<const float4*>(A + (long)(m0 + r) * lda + k0 + kv));
+      if (r < rows && k0 + kv < k_hi) v = __ldg(reinterpret_cast<const float4*>(A + (long)(m0 + r) * lda + k0 + kv));
       *reinterpret_cast<float4*>(&As[r][kv]) = v;
     }
     for (int i = tid; i < kSkK * (SKN / 4); i += 256) {
       const int k = i / (SKN / 4), nv = (i - k * (SKN / 4)) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + k < K && n0 + nv < Nc) v = __ldg(reinterpret_cast<const float4*>(Wt + (long)(k0 + k) * ldw + n0 + nv));
+      if (k0 + k < k_hi && n0 + nv < Nc) v = __ldg(reinterpret_cast<const float4*>(Wt + (long)(k0 + k) * ldw + n0 + nv));
       *reinterpret_cast<float4*>(&Ws[k][nv]) = v;
     }
     __syncthreads();
@@ -584,6 +605,24 @@ skinny_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
         acc[i] = fmaf(a.w, w3, acc[i]);
       }
     }
+  }
+  if (splits > 1) {
+    if (kz != 0) {
+#pragma unroll
+      for (int i = 0; i < kRows; ++i) Part[g + kGroups * i][c] = acc[i];
+    }
+    cluster_sync();                                              // partial tiles written
+    if (kz == 0) {
+      const uint32_t mine = smem_u32(&Part[0][0]);
+      for (int r = 1; r < splits; ++r) {
+        const uint32_t remote = map_to_cluster_rank(mine, r);
+#pragma unroll
+        for (int i = 0; i < kRows; ++i)
+          acc[i] += ld_cluster_f32(remote + ((g + kGroups * i) * SKN + c) * 4);
+      }
+    }
+    cluster_sync();                                              // nobody leaves while its tile is being read
+    if (kz != 0) return;
   }
   const int col = n0 + c;
   if (col >= Nc) return;
@@ -723,13 +762,25 @@ int x3d_head_fc_fwd(const float* A, const float* Wt, const float* bias, float* D
   X3D_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Wt)) & 15) == 0, X3D_ERR_INVALID_ARG, "x3d_head_fc_fwd: pointers must be 16-byte aligned");
   const int my = (M + kSkM - 1) / kSkM;
   X3D_REQUIRE(my <= 65535, X3D_ERR_UNSUPPORTED, "x3d_head_fc_fwd: M too large");
-  if ((long)((Nc + 15) / 16) * my < 96) {          // too few 16-column CTAs to cover the SMs: 4-column tiles
-    dim3 grid((Nc + 3) / 4, my);
-    skinny_gemm_kernel<4><<<grid, 256, 0, S(stream)>>>(A, Wt, bias, D, M, K, Nc, lda, ldw, ldd, relu);
-  } else {
-    dim3 grid((Nc + 15) / 16, my);
-    skinny_gemm_kernel<16><<<grid, 256, 0, S(stream)>>>(A, Wt, bias, D, M, K, Nc, lda, ldw, ldd, relu);
-  }
+  // K split over a cluster: chunks of 64, at most 8 CTAs, at least 2 chunks each
+  int splits = (K + 2 * kSkK - 1) / (2 * kSkK);
+  if (splits > 8) splits = 8;
+  if (splits < 1) splits = 1;
+  const int k_per = ((K + splits - 1) / splits + kSkK - 1) / kSkK * kSkK;
+  splits = (K + k_per - 1) / k_per;
+  const bool narrow = (long)((Nc + 15) / 16) * my * splits < 96;   // too few 16-column CTAs to cover the SMs
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(narrow ? (Nc + 3) / 4 : (Nc + 15) / 16, my, splits);
+  cfg.blockDim = dim3(256);
+  cfg.stream = S(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = splits;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const cudaError_t le = narrow
+      ? cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<4>, A, Wt, bias, D, M, K, Nc, lda, ldw, ldd, relu, k_per)
+      : cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<16>, A, Wt, bias, D, M, K, Nc, lda, ldw, ldd, relu, k_per);
+  X3D_REQUIRE(le == cudaSuccess, X3D_ERR_LAUNCH, "x3d_head_fc_fwd: launch (cluster of %d): %s", splits, cudaGetErrorString(le));
   return check_launch("x3d_head_fc_fwd");
 }
 

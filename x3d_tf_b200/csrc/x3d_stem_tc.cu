@@ -184,17 +184,22 @@ stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const fl
       mbar_wait(&t_full[as], static_cast<uint32_t>((t >> 1) & 1));
       tcgen05_after_sync();
       bf16* dst = dst0 + t * out_frame;
+      // all TMEM reads of the frame first (one wait), so the accumulator is released before the stores
+      uint32_t v[kN / 8][8];
 #pragma unroll
-      for (int c8 = 0; c8 < kN; c8 += 8) {
-        if (c8 < C) {                                   // uniform
-          uint32_t v[8];
-          tmem_ld8(t_lane + as * kN + c8, v);
-          tmem_ld_wait();
-          if (pix_ok) {
+      for (int c8 = 0; c8 < kN; c8 += 8)
+        if (c8 < C) tmem_ld8(t_lane + as * kN + c8, v[c8 / 8]);          // uniform
+      tmem_ld_wait();
+      tcgen05_before_sync();
+      mbar_arrive(&t_empty[as]);
+      if (pix_ok) {
+#pragma unroll
+        for (int c8 = 0; c8 < kN; c8 += 8) {
+          if (c8 < C) {
             float y[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              y[j] = fmaxf(__uint_as_float(v[j]) + s_bias[c8 + j], 0.f);
+              y[j] = fmaxf(__uint_as_float(v[c8 / 8][j]) + s_bias[c8 + j], 0.f);
             __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
             __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
             __nv_bfloat162 p2 = __floats2bfloat162_rn(y[4], y[5]);
@@ -208,8 +213,6 @@ stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const fl
           }
         }
       }
-      tcgen05_before_sync();
-      mbar_arrive(&t_empty[as]);
     };
 
     if constexpr (kStaged) {
@@ -266,12 +269,17 @@ stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const fl
           }
           pk[4] = __byte_perm(w[0][4], w[1][0], 0x7632);
           pk[13] = w[2][4] >> 16;
+          // one 16-byte store per K chunk: row r's chunk sits at r*16, so a warp writes 512 contiguous
+          // bytes (the 4-byte form was a 4-way bank conflict: half of the kernel's shared wavefronts)
           const uint32_t blk = a_s + (i % kRing) * kABytes + a_row;
 #pragma unroll
-          for (int k = 0; k < 28; k += 2)
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(blk + (k >> 3) * (kPix * 16) + (k & 7) * 2),
-                         "r"(pk[k >> 1])
+          for (int kc = 0; kc < 4; ++kc) {
+            const uint32_t v0 = pk[kc * 4], v1 = pk[kc * 4 + 1];
+            const uint32_t v2 = kc < 3 ? pk[kc * 4 + 2] : 0u, v3 = kc < 3 ? pk[kc * 4 + 3] : 0u;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + kc * (kPix * 16)), "r"(v0), "r"(v1),
+                         "r"(v2), "r"(v3)
                          : "memory");
+          }
           fence_proxy_async();
           mbar_arrive(&built[i % kRing]);
           issue_frame(i + 2);
@@ -299,10 +307,15 @@ stem_tc_kernel(const TI* __restrict__ in, const uint4* __restrict__ wc, const fl
       // ---- publish the im2col block of input frame i, then refill the buffer with frame i+2
       const uint32_t blk = a_s + (i % kRing) * kABytes + a_row;
 #pragma unroll
-      for (int k = 0; k < 28; k += 2) {
-        const uint32_t pair = vals[k] | (vals[k + 1] << 16);
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(blk + (k >> 3) * (kPix * 16) + (k & 7) * 2),
-                     "r"(pair)
+      for (int kc = 0; kc < 4; ++kc) {
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = kc * 8 + j * 2;
+          v[j] = k < 28 ? (vals[k] | (vals[k + 1] << 16)) : 0u;
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + kc * (kPix * 16)), "r"(v[0]), "r"(v[1]),
+                     "r"(v[2]), "r"(v[3])
                      : "memory");
       }
       fence_proxy_async();
