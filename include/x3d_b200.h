@@ -189,13 +189,19 @@ int x3d_head_fc_fwd(const float* A, const float* Wt, const float* bias, float* D
  *   Wp   holds the second source's K2 rows at packed column K1 = 64*ceil(K/64) (Kpad >= K1 + 64*ceil(K2/64));
  *   the prologue (se / swish) applies to the first source only; R must be NULL; bias = sum of both shifts.
  * Needs 128-pixel tiles that are whole rows of a frame or whole frames: x3d_pw_tc_sampler_supported
- * (1 / 0); otherwise gather with x3d_gather_rows_fwd and pass the shortcut's result as R. */
+ * (1 / 0); otherwise gather with x3d_gather_rows_fwd and pass the shortcut's result as R.
+ *
+ * Column means (colmean != NULL; conv_5 + pool_5, model.py:117-118): additionally
+ *   colmean[2*i + h, 0:Nc] = (1/64) * sum of the bf16-rounded outputs of rows 128*i + 64*h .. +63 (rows >= M
+ *   contribute 0), fp32 [2*ceil(M/128), Nc]; the mean over the 64-row groups of a clip is the clip's
+ *   global average pool when the clip has a multiple of 64 rows.  store_d = 0 then skips writing D. */
 typedef struct x3d_pw_tc_args {
   const void* A; const void* Wp; const float* bias; const void* R; const float* se; void* D;
   int64_t M; int32_t K, Nc, lda, ldr, ldd, Kpad, Npad;
   int64_t rows_per_clip;
   int32_t swish, relu;
   const void* A2; int64_t a2_nt; int32_t K2, a2_stride, a2_hi, a2_wi;
+  float* colmean; int32_t store_d, reserved;
 } x3d_pw_tc_args;
 int x3d_pw_tc_fwd(const x3d_pw_tc_args* args, void* stream);
 int x3d_pw_tc_sampler_supported(int Hi, int Wi, int stride);

@@ -359,6 +359,26 @@ def test_pointwise_tcgen05_shortcut_as_extra_k(NT, Hi, Wi, K, K2, N, stride, pro
     assert not ops.pw_tc_sampler_supported(112, 112, 2) and not ops.pw_tc_sampler_supported(91, 91, 2)
 
 
+@pytest.mark.parametrize("M,K,N", [(1024, 192, 432), (1000, 96, 56), (130, 24, 280)])
+def test_pointwise_tcgen05_column_means(M, K, N):
+    """conv_5 + pool_5 epilogue: means over 64-row groups of the bf16-rounded output (rows >= M count 0)."""
+    rng = np.random.default_rng(M + N)
+    a = bf16_round(rng.normal(size=(M, K)))
+    w = bf16_round(rng.normal(size=(K, N)) / np.sqrt(K))
+    bias = rng.normal(size=N).astype(np.float32)
+    args = dict(M=M, K=K, Nc=N, relu=True, colmean=True)
+    out, means = _ops().pw_tc_fwd(to_dev(a, torch.bfloat16), _pack_tc(w), to_dev(bias), **args)
+    only = _ops().pw_tc_fwd(to_dev(a, torch.bfloat16), _pack_tc(w), to_dev(bias), store=False, **args)
+    torch.cuda.synchronize()
+    assert_close(to_np(out), _pw_ref(a, w, bias, relu=True), torch.bfloat16, "pw tcgen05 + means")
+    groups = -(-M // 64)
+    padded = np.zeros((groups * 64, N))
+    padded[:M] = to_np(out).astype(np.float64)
+    want = padded.reshape(groups, 64, N).sum(1) / 64
+    np.testing.assert_allclose(to_np(means)[:groups], want, rtol=2e-6, atol=1e-6)
+    assert torch.equal(means[:groups], only[:groups])
+
+
 def test_pointwise_tcgen05_matches_simt_bitwise_inputs():
     """Same bf16 inputs through both pointwise kernels: results agree to bf16 rounding."""
     rng = np.random.default_rng(3)

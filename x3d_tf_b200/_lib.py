@@ -37,7 +37,8 @@ class PwTcArgs(C.Structure):
                 ("ldr", C.c_int32), ("ldd", C.c_int32), ("Kpad", C.c_int32), ("Npad", C.c_int32),
                 ("rows_per_clip", C.c_int64), ("swish", C.c_int32), ("relu", C.c_int32),
                 ("A2", C.c_void_p), ("a2_nt", C.c_int64), ("K2", C.c_int32), ("a2_stride", C.c_int32),
-                ("a2_hi", C.c_int32), ("a2_wi", C.c_int32)]
+                ("a2_hi", C.c_int32), ("a2_wi", C.c_int32),
+                ("colmean", C.c_void_p), ("store_d", C.c_int32), ("reserved", C.c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol include/x3d_b200.h declares.

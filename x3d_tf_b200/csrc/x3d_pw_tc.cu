@@ -12,6 +12,9 @@
 //     (+ residual, prefetched), ReLU, pack bf16 into swizzled staging and TMA-store full lines;
 //   * optional prologue (projection conv, model.py:311-317): 8 transform warps apply
 //     swish(se[clip,k] * a) in place on each landed stage before the MMA consumes it;
+//   * optional column means (conv_5 + pool_5, model.py:117-118): the epilogue also reduces its staged
+//     bf16 tile over rows, 64 at a time, so the global average pool never reads the conv output back
+//     (and with store_d = 0 the output is not even written);
 //   * optional second A source (ResBlock's strided shortcut conv + bn_r, model.py:360-367,386-389):
 //     the K loop continues over the block INPUT, read through a 4-D tensor map whose strides pick
 //     the pixels (t, s*ho, s*wo), against the shortcut's weights stacked under the projection's:
@@ -104,6 +107,9 @@ struct Params {
   int k16_last1;   // K=16 MMAs in the last chunk of the first source
   int a2_ppf;      // second source: output pixels per frame (Ho*Wo), 0 without one
   int a2_wo;       // second source: output row length
+  float* colmean;  // [2*tiles, ldc] means over the 64-row halves of every tile (conv5 + pool), or null
+  int ldc;
+  int store_d;     // 0: D is not written (only the column means are wanted)
   int stages;      // A ring depth
   int tmem_cols;   // power of two >= 2*NT
   int relu, swish;
@@ -340,10 +346,30 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
         X3D_TRACE(5);
-        if (leader) {
+        if (leader && p.store_d) {
           tma_store_2d(&tmD, stage0 + (sub_ctr & 1) * kStageBytes, n0 + sb * 64,
                        static_cast<int>(tile * kBlockM));
           tma_store_commit();
+        }
+        if (p.colmean != nullptr) {
+          // column means of the staged (bf16-rounded) tile: thread = (column, 64-row half); a warp
+          // reads 32 neighbouring columns of one row per load (one 64-byte piece of a swizzled line)
+          const int ccol = r_loc & 63, half = r_loc >> 6;
+          const int col_g = n0 + sb * 64 + ccol;
+          const long row_base = tile * kBlockM + half * 64;
+          int nrows = p.M - row_base < 64 ? static_cast<int>(p.M - row_base) : 64;
+          if (ccol < p.NT - sb * 64 && col_g < p.Nc && nrows > 0) {
+            const uint32_t sbuf = stage0 + (sub_ctr & 1) * kStageBytes;
+            float sum = 0.f;
+            for (int r = 0; r < nrows; ++r) {
+              const int row = half * 64 + r;
+              unsigned short h;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h)
+                           : "r"(sbuf + row * 128 + ((((ccol >> 3) ^ (row & 7)) << 4) | ((ccol & 7) << 1))));
+              sum += __uint_as_float(static_cast<uint32_t>(h) << 16);
+            }
+            p.colmean[(tile * 2 + half) * p.ldc + col_g] = sum * (1.f / 64.f);
+          }
         }
         X3D_TRACE(6);
 #ifdef X3D_PW_TRACE
@@ -508,6 +534,7 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   X3D_REQUIRE(a->Kpad % 64 == 0 && a->Kpad >= a->K && a->Npad % 16 == 0 && a->Npad >= a->Nc,
               X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: bad packed weight extents Kpad=%d Npad=%d", a->Kpad, a->Npad);
   X3D_REQUIRE(!a->se || a->rows_per_clip > 0, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: rows_per_clip missing");
+  X3D_REQUIRE(!a->colmean || (reinterpret_cast<uintptr_t>(a->colmean) & 3) == 0, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: colmean alignment");
   X3D_REQUIRE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->Wp) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(a->D) & 15) == 0, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: pointers must be 16-byte aligned");
   X3D_REQUIRE(device_sm_count() > 0 && device_is_sm100(), X3D_ERR_NO_DEVICE, "x3d_pw_tc_fwd: needs an sm_100 device");
@@ -569,6 +596,7 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   tc::Params p;
   p.bias = a->bias; p.R = static_cast<const bf16*>(a->R); p.se = a->se; p.D = static_cast<bf16*>(a->D);
   p.M = a->M; p.rows_per_clip = a->rows_per_clip; p.Kc = a->K; p.Nc = a->Nc; p.ldr = a->ldr; p.ldd = a->ldd;
+  p.colmean = a->colmean; p.ldc = a->Nc; p.store_d = a->colmean == nullptr || a->store_d;
   p.KC1 = KC1; p.k16_last1 = k16_last1; p.a2_ppf = a->A2 ? a2_ho * a2_wo : 0; p.a2_wo = a2_wo;
   p.NT = NT; p.KC = KC; p.k16_last = k16_last; p.stages = stages; p.tmem_cols = tmem_cols;
   p.relu = a->relu; p.swish = a->swish;

@@ -325,6 +325,9 @@ class Options:
     # (x3d_pw_tc_fwd's second source: no gather kernel, no shortcut GEMM, no residual tensor) wherever
     # 128-pixel tiles align with the output frames (64/32/16/8-wide: every stage at 256^2).
     fold_shortcut = os.environ.get("X3D_FOLD_SHORTCUT", "1") == "1"
+    # bf16 + "tc": conv_5's epilogue also produces the pooled means (no conv_5 output tensor, pool_5 reads
+    # 1/64 of the rows) whenever a clip has a multiple of 64 positions at that point
+    pool_in_conv5 = os.environ.get("X3D_POOL_IN_CONV5", "1") == "1"
     # channelwise 3x3x3 kernel for bf16 activations: "tma" = x3d_dw3x3x3_act_fwd (thread = channel pair,
     # csrc/x3d_dw_tma.cu) everywhere; "auto" = the planar kernel (lanes = pixels, taps in uniform
     # registers, csrc/x3d_dw_planar.cu) for the stride-1 layers wider than 8 pixels that fill >= 90 % of
@@ -703,6 +706,20 @@ class _Conv5(Layer):
         y = self._prep(x.device).run(x, N * T * H * W, use_tc=_use_tc(), relu=True)
         return y.view(N, T, H, W, _pad8(self.cout))
 
+    def _forward_pooled(self, x) -> Optional[torch.Tensor]:
+        """conv_5 + pool_5 (model.py:117-118) in one kernel: the GEMM's epilogue reduces its tiles over
+        rows and the conv output is never written.  [N, pad8(cout)] fp32, or None when this path does
+        not apply (not bf16 / tcgen05, or a clip is not a multiple of 64 positions)."""
+        N, T, H, W, _ = x.shape
+        P = T * H * W
+        if not (_use_tc() and x.dtype == torch.bfloat16 and Options.pool_in_conv5 and P % 64 == 0):
+            return None
+        ops.Profiler.tag = "conv5"
+        pc = self._prep(x.device)
+        means = ops.pw_tc_fwd(x, pc.wp, pc.bias, M=N * P, K=pc.Ks, Nc=pc.Ns, relu=True, colmean=True, store=False)
+        ops.Profiler.tag = "head_pool"
+        return ops.avgpool_fwd(means[:N * P // 64].view(N, P // 64, pc.Ns))
+
 
 class _Dense(Layer):
     def __init__(self, name, key_shape, bias: bool):
@@ -780,9 +797,11 @@ class X3D(Layer):
         out = self.conv1._forward(x, act_dtype)
         for st in self.stages:
             out = st._forward(out)
-        out = self.conv5._forward(out)
-        ops.Profiler.tag = "head_pool"
-        pooled = ops.avgpool_fwd(out)                                   # [N, C5s] fp32
+        pooled = self.conv5._forward_pooled(out)                        # [N, C5s] fp32
+        if pooled is None:
+            out = self.conv5._forward(out)
+            ops.Profiler.tag = "head_pool"
+            pooled = ops.avgpool_fwd(out)
         N = pooled.shape[0]
         ops.Profiler.tag = "head_fc"
         f1 = self.fc1._prep(x.device)
@@ -809,7 +828,7 @@ class X3D(Layer):
         over their own input/output buffers that share slot 0's memory pool (replays are
         stream-ordered), used by `predict` to overlap the H2D copy of the next batch."""
         key = (tuple(shape), dtype, str(device), Options.pointwise, Options.stem, Options.stem_u8, Options.swish_in_dw,
-               Options.fuse_expand, Options.channelwise, Options.fold_shortcut, slot)
+               Options.fuse_expand, Options.channelwise, Options.fold_shortcut, Options.pool_in_conv5, slot)
         if key not in self._graphs:
             static_in = torch.zeros(tuple(shape), dtype=dtype, device=device)
             self._forward(static_in, training)

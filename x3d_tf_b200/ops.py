@@ -192,17 +192,25 @@ def pw_fwd(a: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], *, M
 def pw_tc_fwd(a: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], *, M: int, K: int,
               Nc: int, out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
               se: Optional[torch.Tensor] = None, rows_per_clip: int = 0, swish: bool = False,
-              relu: bool = False, a2: Optional[torch.Tensor] = None, a2_stride: int = 1) -> torch.Tensor:
+              relu: bool = False, a2: Optional[torch.Tensor] = None, a2_stride: int = 1,
+              colmean: bool = False, store: bool = True):
     """tcgen05 pointwise GEMM (bf16).  `wp` is the packed [Npad, Kpad] bf16 weight.
-    `a2` [N,T,Hi,Wi,K2]: second K source sampled at (t, s*ho, s*wo) -- the shortcut conv folded in."""
+    `a2` [N,T,Hi,Wi,K2]: second K source sampled at (t, s*ho, s*wo) -- the shortcut conv folded in.
+    `colmean`: also return the fp32 means over 64-row groups [2*ceil(M/128), Nc] (conv_5 + pool_5);
+    with `store=False` the GEMM output itself is not written and only the means are returned."""
     _req(a, "a")
     if a.dtype != torch.bfloat16:
         raise TypeError("pw_tc_fwd needs bf16 activations")
+    if not store and not colmean:
+        raise ValueError("pw_tc_fwd: store=False only together with colmean=True")
     if out is None:
-        out = torch.empty((M, Nc), dtype=torch.bfloat16, device=a.device)
+        # (the kernel still wants a valid D for its tensor map; without a store one row is enough)
+        out = torch.empty((M if store else 128, Nc), dtype=torch.bfloat16, device=a.device)
+    means = torch.empty((2 * -(-M // 128), Nc), dtype=torch.float32, device=a.device) if colmean else None
     args = PwTcArgs()
     args.A, args.Wp, args.bias = a.data_ptr(), wp.data_ptr(), _ptr(bias)
     args.R, args.se, args.D = _ptr(residual), _ptr(se), out.data_ptr()
+    args.colmean, args.store_d = _ptr(means), int(store)
     args.M, args.K, args.Nc = M, K, Nc
     args.lda, args.ldr, args.ldd = K, Nc, Nc
     args.Npad, args.Kpad = wp.shape
@@ -215,6 +223,8 @@ def pw_tc_fwd(a: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], *
         args.A2, args.a2_nt, args.K2 = a2.data_ptr(), a2.shape[0] * a2.shape[1], a2.shape[4]
         args.a2_stride, args.a2_hi, args.a2_wi = a2_stride, a2.shape[2], a2.shape[3]
     _launch("x3d_pw_tc_fwd", lambda: lib().x3d_pw_tc_fwd(args, _stream()))
+    if colmean:
+        return (out, means) if store else means
     return out
 
 
