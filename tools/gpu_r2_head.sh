@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_model.py tests/test_reference_golden.py -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/r2_head_pytest.txt
+timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_model.py tests/test_reference_golden.py tests/test_gpu_training.py -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/r2_head_pytest.txt
 timeout 600 python bench.py --steps 10 --warmup 3 --no-configs > gpurun_out/r2_bench_head.json 2> gpurun_out/r2_bench_head.err
 python - <<PY
 import json

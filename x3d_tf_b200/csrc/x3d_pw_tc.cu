@@ -115,7 +115,13 @@ struct Params {
   int relu, swish;
 };
 
-constexpr int kEpiWarps = 8, kProWarps = 8, kOutBufs = 4;   // 2 epilogue groups x 2 staging buffers
+constexpr int kEpiWarps = 8, kProWarps = 8, kOutBufs = 4;
+// transform groups (each takes every kProGroups-th stage).  The A ring must be at least this deep: a group's
+// FIRST wait has to be on the ring's first pass (a parity wait cannot tell pass 1 from 'never filled').
+// Measured (stage 2 / 3 / 4 projection with SE, 80 clips): 1 group 0.267 / 0.130 / 0.078 ms, 2 groups
+// 0.234 / 0.122 / 0.076, 4 groups 0.229 / 0.121 / 0.073 (and needs 4 stages, which K = 432 does not leave).
+constexpr int kProGroups = 2;
+constexpr int kProRows = 8 * kProWarps / kProGroups / 2;   // row stride of a transform thread: (threads per group) / 8   // 2 epilogue groups x 2 staging buffers
 constexpr int kThreadsPlain = 64 + 32 * kEpiWarps, kThreadsPro = kThreadsPlain + 32 * kProWarps;
 
 template <bool kPro>
@@ -155,7 +161,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
-      mbar_init(&xform[s], 32 * kProWarps);
+      mbar_init(&xform[s], 32 * kProWarps / kProGroups);   // one transform group per stage
     }
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -379,52 +385,86 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     if (leader) tma_store_wait_read<0>();
   } else if (kPro) {
-    // ------------------------------------------------------------------ prologue transform (8 warps)
-    // In place on the landed stage: a <- swish(se[clip, k] * a).  A thread owns one physical
-    // 16-byte chunk column (8 channels) of rows tt/8 + 32*i; because 32 is a multiple of the
-    // swizzle period its channel offset k is the same for all 4 rows, so the 8 SE factors are
-    // fetched once per stage (tiles that straddle two clips take the per-row path).  The 4 shared
-    // loads are issued back to back before any math so their latency overlaps.
+    // ------------------------------------------------------------------ prologue transform (2 x 4 warps)
+    // In place on the landed stage: a <- swish(se[clip, k] * a).  The two groups of four warps take
+    // alternate stages, so one group's load -> MUFU -> store -> proxy fence -> arrive chain overlaps
+    // the other's (with all eight warps on one stage that chain was the kernel's critical path).
+    // A thread owns one physical 16-byte chunk column (8 channels) of rows rbase + 16*i; 16 is a
+    // multiple of the swizzle period, so its channel offset k is the same for all 8 rows and the 8 SE
+    // factors are fetched once per stage -- requested one stage of the group ahead (the L2 round trip
+    // was 17 % of these warps' time); tiles that straddle two clips take the per-row path.
     const int tt = threadIdx.x - kThreadsPlain;   // 0..255
+    constexpr int kGT = 32 * kProWarps / kProGroups;          // threads per group
+    const int grp = tt / kGT;                     // the stages j with j % kProGroups == grp are this thread's
     const int pchunk = tt & 7;                    // physical 16-byte chunk inside the 128-byte row
-    const int rbase = tt >> 3;                    // 0..31
+    const int rbase = (tt % kGT) >> 3;            // 0 .. kGT/8-1 (a multiple of 8 rows apart: same swizzle phase)
     const int kin = (pchunk ^ (rbase & 7)) << 3;  // channel offset inside the 64-wide chunk
     const uint32_t rpc = static_cast<uint32_t>(p.rows_per_clip > 0 ? p.rows_per_clip : 0x7fffffff);
+    const uint32_t step = static_cast<uint32_t>(gridDim.x) * kBlockM;
+    // position of a stage: (tile, K chunk) and (clip, row inside the clip) of the tile's first row,
+    // advanced without divisions
+    struct Pos { long tile; int kc; uint32_t clip, rem; };
+    auto advance = [&](Pos& q) {
+      if (++q.kc == p.KC) {
+        q.kc = 0;
+        q.tile += gridDim.x;
+        q.rem += step;
+        while (q.rem >= rpc) { q.rem -= rpc; ++q.clip; }
+      }
+    };
+    auto se_request = [&](const Pos& q, float4& s0, float4& s1) {
+      s0 = make_float4(1.f, 1.f, 1.f, 1.f);
+      s1 = s0;
+      const int k = q.kc * kBlockK + kin;
+      if (p.se != nullptr && q.tile < num_tiles && k < p.Kc && q.kc < p.KC1 && q.rem + kBlockM <= rpc) {
+        const float4* sp = reinterpret_cast<const float4*>(p.se + static_cast<long>(q.clip) * p.Kc + k);
+        s0 = __ldg(sp);
+        s1 = __ldg(sp + 1);
+      }
+    };
+    Pos cur;
+    cur.tile = blockIdx.x; cur.kc = 0;
+    cur.clip = static_cast<uint32_t>(blockIdx.x * static_cast<long>(kBlockM) / rpc);
+    cur.rem = static_cast<uint32_t>(blockIdx.x * static_cast<long>(kBlockM) - static_cast<long>(cur.clip) * rpc);
     int s = 0;
     uint32_t ph = 0;
-    for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const uint32_t row0 = static_cast<uint32_t>(tile * kBlockM);
-      const uint32_t clip0 = row0 / rpc, rem0 = row0 - clip0 * rpc;
+    for (int g = 0; g < grp; ++g) {
+      advance(cur);
+      if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
+    float4 nx0, nx1;
+    se_request(cur, nx0, nx1);
+    while (cur.tile < num_tiles) {
+      const uint32_t clip0 = cur.clip, rem0 = cur.rem;
       const bool one_clip = rem0 + kBlockM <= rpc;            // whole tile inside one clip
-      for (int kc = 0; kc < p.KC; ++kc) {
-        const int k = kc * kBlockK + kin;
-        // beyond Kc the stage holds TMA zeros; chunks of the second source are not transformed
-        const bool k_ok = k < p.Kc && kc < p.KC1;
-        float2 sc[4];
+      const int k = cur.kc * kBlockK + kin;
+      // beyond Kc the stage holds TMA zeros; chunks of the second source are not transformed
+      const bool k_ok = k < p.Kc && cur.kc < p.KC1;
+      float2 sc[4];
+      sc[0] = make_float2(nx0.x, nx0.y); sc[1] = make_float2(nx0.z, nx0.w);
+      sc[2] = make_float2(nx1.x, nx1.y); sc[3] = make_float2(nx1.z, nx1.w);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sc[j] = make_float2(1.f, 1.f);
-        if (p.se && k_ok && one_clip) {
-          const float4* sp = reinterpret_cast<const float4*>(p.se + static_cast<long>(clip0) * p.Kc + k);
-          const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
-          sc[0] = make_float2(s0.x, s0.y); sc[1] = make_float2(s0.z, s0.w);
-          sc[2] = make_float2(s1.x, s1.y); sc[3] = make_float2(s1.z, s1.w);
-        }
-        mbar_wait(&full[s], ph);
-        if (k_ok) {
-          const uint32_t addr0 = smem_u32(sA + s * kStageBytes) + rbase * 128 + pchunk * 16;
+      for (int g = 0; g < kProGroups; ++g) advance(cur);
+      se_request(cur, nx0, nx1);
+      mbar_wait(&full[s], ph);
+      if (k_ok) {
+        const uint32_t addr0 = smem_u32(sA + s * kStageBytes) + rbase * 128 + pchunk * 16;
+        float2 hs[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hs[j] = __fmul2_rn(sc[j], make_float2(0.5f, 0.5f));
+#pragma unroll
+        for (int half = 0; half < kBlockM / (kGT / 8) / 4; ++half) {
+          // four rows at a time: their shared loads are issued back to back before any math
           uint32_t w[4][4];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(w[i][0]), "=r"(w[i][1]), "=r"(w[i][2]), "=r"(w[i][3])
-                         : "r"(addr0 + i * (32 * 128)));
-          float2 hs[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) hs[j] = __fmul2_rn(sc[j], make_float2(0.5f, 0.5f));
+                         : "r"(addr0 + (half * 4 + i) * (kGT / 8 * 128)));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             if (p.se && !one_clip) {
-              uint32_t x = rem0 + rbase + 32 * i, clip = clip0;
+              uint32_t x = rem0 + rbase + (kGT / 8) * (half * 4 + i), clip = clip0;
               while (x >= rpc) { x -= rpc; ++clip; }
               if (static_cast<long>(clip) * rpc + x < p.M) {
                 const float4* sp = reinterpret_cast<const float4*>(p.se + static_cast<long>(clip) * p.Kc + k);
@@ -449,18 +489,20 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             } else {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
+                const float2 scj = make_float2(2.f * hs[j].x, 2.f * hs[j].y);
                 __nv_bfloat162 t2 = __float22bfloat162_rn(__fmul2_rn(
-                    make_float2(__uint_as_float(w[i][j] << 16), __uint_as_float(w[i][j] & 0xffff0000u)), sc[j]));
+                    make_float2(__uint_as_float(w[i][j] << 16), __uint_as_float(w[i][j] & 0xffff0000u)), scj));
                 w[i][j] = *reinterpret_cast<uint32_t*>(&t2);
               }
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr0 + i * (32 * 128)), "r"(w[i][0]), "r"(w[i][1]), "r"(w[i][2]), "r"(w[i][3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr0 + (half * 4 + i) * (kGT / 8 * 128)), "r"(w[i][0]), "r"(w[i][1]), "r"(w[i][2]), "r"(w[i][3]) : "memory");
           }
         }
-        fence_proxy_async();
-        mbar_arrive(&xform[s]);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
+      fence_proxy_async();
+      mbar_arrive(&xform[s]);
+      s += kProGroups;
+      while (s >= p.stages) { s -= p.stages; ph ^= 1; }
     }
   }
 
@@ -571,7 +613,7 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
     stages = (budget - wbytes) / tc::kStageBytes;
     if (stages >= 3 || NT <= 64) break;
   }
-  X3D_REQUIRE(stages >= 2, X3D_ERR_UNSUPPORTED, "x3d_pw_tc_fwd: K=%d too large for shared memory", a->K);
+  X3D_REQUIRE(stages >= 2 && stages >= tc::kProGroups, X3D_ERR_UNSUPPORTED, "x3d_pw_tc_fwd: K=%d too large for shared memory", a->K);
   if (stages > 8) stages = 8;
   n_tiles = (a->Nc + NT - 1) / NT;                     // tiles that hold real columns
   int tmem_cols = 32;
