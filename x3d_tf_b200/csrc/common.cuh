@@ -44,6 +44,28 @@ inline cudaError_t ensure_dynamic_smem(Kern kern, SmemOptIn& state, size_t bytes
   return cudaSuccess;
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// A kernel launched through launch_pdl may start while its predecessor in the stream is still
+// running: its CTAs become resident as the predecessor's retire, run their set-up (barriers, TMEM,
+// tensor-map prefetch, weight loads -- nothing the predecessor writes), and block in pdl_wait()
+// until the predecessor grid has completed and its memory is visible.  pdl_trigger() lets the NEXT
+// kernel's CTAs be scheduled.  Rule for every kernel launched this way: no access to activations
+// (reads of inputs, writes of outputs) before pdl_wait().  X3D_PDL=0 turns the attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();   // host_util.cu
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- two-channel (the unit a channelwise thread owns) and vector loads/stores ----
 __device__ __forceinline__ float2 ld2(const float* p) {
   return __ldg(reinterpret_cast<const float2*>(p));

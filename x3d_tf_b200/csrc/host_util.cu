@@ -1,5 +1,6 @@
 // Host-side pieces of the C ABI: error text, version, CRC-32C.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -38,6 +39,14 @@ struct CrcTables {
       for (int s = 1; s < 8; ++s) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xff];
   }
 };
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("X3D_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
 
 EncodeTiledFn tensor_map_encoder() {
   static EncodeTiledFn fn = nullptr;

@@ -156,6 +156,10 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     fence_barrier_init();
   }
   __syncthreads();
+  // (launch_pdl) input tiles, output stores and the SE sums all come after this point; every CTA of the
+  // persistent grid is resident, so the next kernel may be scheduled as soon as SMs free up
+  pdl_wait();
+  pdl_trigger();
 
   // item -> (clip, tile, chunk), the chunk fastest: neighbouring CTAs share the input tile in L2
   auto decode = [&](int idx, int& n, int& tile, int& chunk, int& ho0, int& wo0) {
@@ -409,7 +413,11 @@ static int launch(const CUtensorMap& ti, const CUtensorMap& to, const Params& p,
   const long total = (long)N * pl.tiles_w * pl.tiles_h * pl.chunks;
   long gx = 2L * device_sm_count();
   if (gx > total) gx = total;
-  kern<<<(unsigned)gx, kThreads, G::smem, st>>>(ti, to, p);
+  const cudaError_t le = launch_pdl(kern, dim3((unsigned)gx), dim3(kThreads), G::smem, st, ti, to, p);
+  if (le != cudaSuccess) {
+    set_error("x3d_dw3x3x3_planar_fwd: launch: %s", cudaGetErrorString(le));
+    return X3D_ERR_LAUNCH;
+  }
   return check_launch("x3d_dw3x3x3_planar_fwd");
 }
 

@@ -107,6 +107,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();                                  // (launch_pdl) the input is the previous kernel's output
   if (tid == 0) {
     for (int f = 0; f < kSlots && f < p.T; ++f) {
       mbar_expect_tx(&full[f], static_cast<uint32_t>(p.box_bytes));
@@ -234,6 +235,8 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
   if (rem == 0) stage_out(acc[2], p.T - 1);
   else if (rem == 1) stage_out(acc[0], p.T - 1);
   else stage_out(acc[1], p.T - 1);
+  // many waves of CTAs: let the next kernel's CTAs in only now, when this one is about to leave
+  pdl_trigger();
   if (p.partial != nullptr && in_slot) {
     s_red[slot * CH + 2 * cp] = ssum.x;
     s_red[slot * CH + 2 * cp + 1] = ssum.y;
@@ -311,7 +314,11 @@ static int launch(const CUtensorMap& tm, const CUtensorMap& tmo, const Params& p
     return X3D_ERR_LAUNCH;
   }
   dim3 grid(pl.tiles_w * pl.tiles_h, pl.chunks, N);
-  kern<<<grid, pl.threads, pl.smem, st>>>(tm, tmo, p);
+  const cudaError_t le = launch_pdl(kern, grid, dim3(pl.threads), pl.smem, st, tm, tmo, p);
+  if (le != cudaSuccess) {
+    set_error("x3d_dw3x3x3_fwd: launch: %s", cudaGetErrorString(le));
+    return X3D_ERR_LAUNCH;
+  }
   return check_launch("x3d_dw3x3x3_fwd");
 }
 

@@ -184,12 +184,16 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const long num_tiles = (p.M + kBlockM - 1) / kBlockM;
 
+  // Programmatic dependent launch: everything above (and the weight fetch below) touches nothing the
+  // previous kernel of the stream writes; activations are only accessed after pdl_wait().
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       mbar_expect_tx(w_full, static_cast<uint32_t>(p.KC * w_chunk_bytes));
       for (int kc = 0; kc < p.KC; ++kc)
         tma_load_2d(sW + kc * w_chunk_bytes, &tmW, kc * kBlockK, n0, w_full);
+      pdl_wait();
+      pdl_trigger();
       int s = 0;
       uint32_t ph = 0;
       for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -211,6 +215,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    pdl_trigger();                                // (reads only what the producer loads after its own wait)
     const uint32_t idesc = make_idesc_bf16(p.NT);
     mbar_wait(w_full, 0);
     int s = 0;
@@ -244,6 +249,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // Group g owns TMEM accumulator g and every second tile, so two epilogues are in flight; inside
     // a group warp w reads TMEM lane quarter w%4.  Results are staged in 128B-swizzled shared
     // memory and leave as full lines through TMA box stores (clipped at M / Nc).
+    pdl_wait();                                   // residual rows / output stores
+    pdl_trigger();
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int grp = (warp - 2) >> 2;
     const bool leader = q == 2 && lane == 0;      // first warp of each group is warp 2 / warp 6
@@ -393,6 +400,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // multiple of the swizzle period, so its channel offset k is the same for all 8 rows and the 8 SE
     // factors are fetched once per stage -- requested one stage of the group ahead (the L2 round trip
     // was 17 % of these warps' time); tiles that straddle two clips take the per-row path.
+    pdl_wait();                                   // the SE factors come from the previous kernel
+    pdl_trigger();
     const int tt = threadIdx.x - kThreadsPlain;   // 0..255
     constexpr int kGT = 32 * kProWarps / kProGroups;          // threads per group
     const int grp = tt / kGT;                     // the stages j with j % kProGroups == grp are this thread's
@@ -656,11 +665,13 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   if (pro) {
     e = ensure_dynamic_smem(tc::pw_tc_kernel<true>, optin_pro, smem, false);
     X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
-    tc::pw_tc_kernel<true><<<grid, tc::kThreadsPro, smem, st>>>(tmA, tmW, tmD, tmA2, p);
+    e = launch_pdl(tc::pw_tc_kernel<true>, grid, dim3(tc::kThreadsPro), smem, st, tmA, tmW, tmD, tmA2, p);
+    X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: launch: %s", cudaGetErrorString(e));
   } else {
     e = ensure_dynamic_smem(tc::pw_tc_kernel<false>, optin_plain, smem, false);
     X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: smem attribute: %s", cudaGetErrorString(e));
-    tc::pw_tc_kernel<false><<<grid, tc::kThreadsPlain, smem, st>>>(tmA, tmW, tmD, tmA2, p);
+    e = launch_pdl(tc::pw_tc_kernel<false>, grid, dim3(tc::kThreadsPlain), smem, st, tmA, tmW, tmD, tmA2, p);
+    X3D_REQUIRE(e == cudaSuccess, X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: launch: %s", cudaGetErrorString(e));
   }
   return check_launch("x3d_pw_tc_fwd");
 }

@@ -125,6 +125,8 @@ se_mlp_kernel(const float* __restrict__ partial, int nblk, float inv_count,
   float* z = sm + C;
   float* red = z + Cw;
   const int n = blockIdx.x, tid = threadIdx.x;
+  pdl_wait();                                   // (launch_pdl) the tile sums are the previous kernel's output
+  pdl_trigger();
   const float* p = partial + (long)n * nblk * C;
   // tile sums -> mean: the tiles of a channel are split over KG thread groups (independent,
   // coalesced loads; up to 64 tiles at the stage-2 resolution), combined in fixed order
@@ -677,8 +679,9 @@ int x3d_se_mlp_fwd(const float* partial, int nblk, float inv_count, const float*
                    int Cw, void* stream) {
   X3D_REQUIRE(partial && w1 && b1 && w2 && b2 && scale, X3D_ERR_INVALID_ARG, "x3d_se_mlp_fwd: null pointer");
   X3D_REQUIRE(N > 0 && C > 0 && Cw > 0 && Cw <= 64 && nblk > 0, X3D_ERR_INVALID_ARG, "x3d_se_mlp_fwd: bad size");
-  se_mlp_kernel<<<N, 256, sizeof(float) * (C + Cw + 256), S(stream)>>>(partial, nblk, inv_count, w1, b1,
-                                                               w2, b2, scale, C, Cw);
+  const cudaError_t le = launch_pdl(se_mlp_kernel, dim3(N), dim3(256), sizeof(float) * (C + Cw + 256), S(stream), partial,
+                                    nblk, inv_count, w1, b1, w2, b2, scale, C, Cw);
+  X3D_REQUIRE(le == cudaSuccess, X3D_ERR_LAUNCH, "x3d_se_mlp_fwd: launch: %s", cudaGetErrorString(le));
   return check_launch("x3d_se_mlp_fwd");
 }
 
