@@ -113,6 +113,7 @@ struct Params {
   int stages;      // A ring depth
   int tmem_cols;   // power of two >= 2*NT
   int relu, swish;
+  int contiguous;  // tile assignment (see the kernel)
 };
 
 constexpr int kEpiWarps = 8, kProWarps = 8, kOutBufs = 4;
@@ -182,7 +183,17 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Tiles of this CTA: tile_lo, tile_lo + t_stride, ... < tile_hi.  Plain GEMMs interleave the CTAs
+  // (t_stride = grid: the 148 CTAs sweep one window of memory together); with the SE prologue a CTA takes
+  // one contiguous range, so it stays inside one or two clips and their scale vectors stay cached.
   const long num_tiles = (p.M + kBlockM - 1) / kBlockM;
+  long tile_lo = blockIdx.x, tile_hi = num_tiles, t_stride = gridDim.x;
+  if (p.contiguous) {
+    const long t_per = num_tiles / gridDim.x, t_rem = num_tiles % gridDim.x;
+    tile_lo = blockIdx.x * t_per + (blockIdx.x < t_rem ? blockIdx.x : t_rem);
+    tile_hi = tile_lo + t_per + (blockIdx.x < t_rem ? 1 : 0);
+    t_stride = 1;
+  }
 
   // Programmatic dependent launch: everything above (and the weight fetch below) touches nothing the
   // previous kernel of the stream writes; activations are only accessed after pdl_wait().
@@ -196,7 +207,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       pdl_trigger();
       int s = 0;
       uint32_t ph = 0;
-      for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (long tile = tile_lo; tile < tile_hi; tile += t_stride) {
         const int row0 = static_cast<int>(tile * kBlockM);
         // second source: the tile's 128 output pixels are whole rows of one frame (or whole frames)
         int nt0 = 0, ho0 = 0;
@@ -221,7 +232,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int s = 0;
     uint32_t ph = 0;
     long it = 0;
-    for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (long tile = tile_lo; tile < tile_hi; tile += t_stride, ++it) {
       const int as = static_cast<int>(it & 1);
       const uint32_t aph = static_cast<uint32_t>((it >> 1) & 1);
       mbar_wait(&t_empty[as], aph ^ 1);
@@ -267,8 +278,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const bool trace_on = blockIdx.x == 7 && blockIdx.y == 0 && grp == 0 && leader;
     int trace_n = 0;
 #endif
-    for (long tile = blockIdx.x + static_cast<long>(grp) * gridDim.x; tile < num_tiles;
-         tile += 2L * gridDim.x, aph ^= 1) {
+    for (long tile = tile_lo + grp * t_stride; tile < tile_hi; tile += 2 * t_stride, aph ^= 1) {
       X3D_TRACE(0);
       const long row = tile * kBlockM + r_loc;
       const bool row_ok = row < p.M;
@@ -282,8 +292,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // The residual rows come from DRAM (several kernels ago) and their latency is exposed in the
       // drain below (timeline: tools/trace_pw.py): pull the NEXT tile's rows of this group into L2 now
       if (p.R) {
-        const long nrow = row + 2L * gridDim.x * kBlockM;
-        if (nrow < p.M) {
+        const long nrow = row + 2L * t_stride * kBlockM;
+        if (nrow < p.M && tile + 2 * t_stride < tile_hi) {
           const char* np_ = reinterpret_cast<const char*>(p.R + nrow * p.ldr + n0);
           for (int off = 0; off < p.NT * 2; off += 128)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + off));
@@ -409,14 +419,14 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int rbase = (tt % kGT) >> 3;            // 0 .. kGT/8-1 (a multiple of 8 rows apart: same swizzle phase)
     const int kin = (pchunk ^ (rbase & 7)) << 3;  // channel offset inside the 64-wide chunk
     const uint32_t rpc = static_cast<uint32_t>(p.rows_per_clip > 0 ? p.rows_per_clip : 0x7fffffff);
-    const uint32_t step = static_cast<uint32_t>(gridDim.x) * kBlockM;
+    const uint32_t step = static_cast<uint32_t>(t_stride) * kBlockM;
     // position of a stage: (tile, K chunk) and (clip, row inside the clip) of the tile's first row,
     // advanced without divisions
     struct Pos { long tile; int kc; uint32_t clip, rem; };
     auto advance = [&](Pos& q) {
       if (++q.kc == p.KC) {
         q.kc = 0;
-        q.tile += gridDim.x;
+        q.tile += t_stride;
         q.rem += step;
         while (q.rem >= rpc) { q.rem -= rpc; ++q.clip; }
       }
@@ -425,16 +435,16 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       s0 = make_float4(1.f, 1.f, 1.f, 1.f);
       s1 = s0;
       const int k = q.kc * kBlockK + kin;
-      if (p.se != nullptr && q.tile < num_tiles && k < p.Kc && q.kc < p.KC1 && q.rem + kBlockM <= rpc) {
+      if (p.se != nullptr && q.tile < tile_hi && k < p.Kc && q.kc < p.KC1 && q.rem + kBlockM <= rpc) {
         const float4* sp = reinterpret_cast<const float4*>(p.se + static_cast<long>(q.clip) * p.Kc + k);
         s0 = __ldg(sp);
         s1 = __ldg(sp + 1);
       }
     };
     Pos cur;
-    cur.tile = blockIdx.x; cur.kc = 0;
-    cur.clip = static_cast<uint32_t>(blockIdx.x * static_cast<long>(kBlockM) / rpc);
-    cur.rem = static_cast<uint32_t>(blockIdx.x * static_cast<long>(kBlockM) - static_cast<long>(cur.clip) * rpc);
+    cur.tile = tile_lo; cur.kc = 0;
+    cur.clip = static_cast<uint32_t>(tile_lo * static_cast<long>(kBlockM) / rpc);
+    cur.rem = static_cast<uint32_t>(tile_lo * static_cast<long>(kBlockM) - static_cast<long>(cur.clip) * rpc);
     int s = 0;
     uint32_t ph = 0;
     for (int g = 0; g < grp; ++g) {
@@ -443,7 +453,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     float4 nx0, nx1;
     se_request(cur, nx0, nx1);
-    while (cur.tile < num_tiles) {
+    while (cur.tile < tile_hi) {
       const uint32_t clip0 = cur.clip, rem0 = cur.rem;
       const bool one_clip = rem0 + kBlockM <= rpc;            // whole tile inside one clip
       const int k = cur.kc * kBlockK + kin;
@@ -651,6 +661,7 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   p.KC1 = KC1; p.k16_last1 = k16_last1; p.a2_ppf = a->A2 ? a2_ho * a2_wo : 0; p.a2_wo = a2_wo;
   p.NT = NT; p.KC = KC; p.k16_last = k16_last; p.stages = stages; p.tmem_cols = tmem_cols;
   p.relu = a->relu; p.swish = a->swish;
+  p.contiguous = a->se != nullptr ? 1 : 0;
 
   const size_t smem = 1024 + (size_t)KC * NT * 128 + (size_t)(stages + tc::kOutBufs) * tc::kStageBytes + 1024 + 512;
   const long num_tiles = (a->M + tc::kBlockM - 1) / tc::kBlockM;
