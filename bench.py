@@ -459,7 +459,7 @@ def run_b200(args):
     # utils.normalize (dataloader.py:93-121, utils.py:42-72); the normalisation runs on the device.
     e2e = None
     if not args.no_e2e:
-        n_e2e = max(3, min(args.steps, 10))
+        n_e2e = max(3, min(args.steps, 30))      # (the first step's copy is not overlapped: more steps amortise it)
         if tdt == torch.bfloat16:
             g8 = torch.Generator()
             g8.manual_seed(2222 + rank)

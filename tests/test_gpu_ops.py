@@ -112,7 +112,8 @@ def test_channelwise(dtype, N, T, H, W, C, stride):
 
 
 @pytest.mark.parametrize("N,T,H,W,C,stride", DW_CASES + [(3, 4, 64, 64, 56, 1), (2, 16, 33, 70, 24, 1), (2, 5, 64, 64, 56, 2),
-                                                        (5, 3, 8, 8, 432, 1), (2, 7, 16, 16, 216, 2)])
+                                                        (5, 3, 8, 8, 432, 1), (2, 7, 16, 16, 216, 2), (2, 4, 56, 56, 56, 1),
+                                                        (3, 5, 28, 28, 112, 1), (3, 6, 14, 14, 216, 1)])   # 7 rows per thread
 def test_channelwise_planar(N, T, H, W, C, stride):
     """x3d_dw3x3x3_planar_fwd (lanes = pixels, taps in uniform registers) against the same oracle as
     x3d_dw3x3x3_fwd: output, SE partial sums, swish epilogue; several clips / tiles / chunks per CTA."""
@@ -330,12 +331,14 @@ def test_pointwise_tcgen05_prologue_epilogue():
     (5, 16, 16, 432, 96, 192, 2, False),     # odd frame count: last tile half outside the tensor
     (3, 127, 128, 56, 24, 24, 2, True),      # odd height: Ho = 64, last sampled row is 126
     (2, 64, 64, 56, 24, 24, 1, True),        # stride 1 (channel change only)
+    (3, 30, 44, 112, 24, 48, 2, True),       # 15x22 frames: no aligned tiles -> gathered rows as a dense second source
 ])
 def test_pointwise_tcgen05_shortcut_as_extra_k(NT, Hi, Wi, K, K2, N, stride, pro):
     """x3d_pw_tc_fwd's second source: relu(bias + pro(A).W + sample(X).W2) against the fp64 formula."""
     rng = np.random.default_rng(NT * Hi + K)
     ops = _ops()
-    assert ops.pw_tc_sampler_supported(Hi, Wi, stride)
+    sampled = ops.pw_tc_sampler_supported(Hi, Wi, stride)
+    assert sampled == (Wi != 44)
     Ho, Wo = (Hi - 1) // stride + 1, (Wi - 1) // stride + 1
     M = NT * Ho * Wo
     a = bf16_round(rng.normal(size=(M, K)))
@@ -351,7 +354,8 @@ def test_pointwise_tcgen05_shortcut_as_extra_k(NT, Hi, Wi, K, K2, N, stride, pro
     se = rng.uniform(0.1, 0.9, size=(-(-M // rpc), K)).astype(np.float32) if pro else None
     got = ops.pw_tc_fwd(to_dev(a, torch.bfloat16), to_dev(wp, torch.bfloat16), to_dev(bias), M=M, K=K, Nc=N,
                         se=to_dev(se) if pro else None, rows_per_clip=rpc if pro else 0, swish=pro, relu=True,
-                        a2=to_dev(x, torch.bfloat16), a2_stride=stride)
+                        a2=to_dev(x, torch.bfloat16) if sampled else ops.gather_rows_fwd(to_dev(x, torch.bfloat16), stride),
+                        a2_stride=stride)
     torch.cuda.synchronize()
     xs = x[0, :, ::stride, ::stride, :].reshape(M, K2).astype(np.float64)
     want = _pw_ref(a, w, bias, xs @ w2.astype(np.float64), se, rpc, pro, True)

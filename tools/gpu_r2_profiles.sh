@@ -5,9 +5,8 @@ cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
 mkdir -p gpurun_out
 B="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-configs"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_bench.csv $B > gpurun_out/r2_launches_bench.log 2>&1
-python tools/launch_summary.py gpurun_out/r2_launches_bench.csv 105 > gpurun_out/r2_launches_bench_summary.txt; head -16 gpurun_out/r2_launches_bench_summary.txt
-timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:dw_tma --csv --log-file gpurun_out/r2_dw_traffic.csv $B > gpurun_out/r2_dw_traffic.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:dw_tma -s 130 -c 3 -o gpurun_out/r2_dw_tma -f $B > gpurun_out/r2_ncu_dw.log 2>&1
+python tools/launch_summary.py gpurun_out/r2_launches_bench.csv 97 > gpurun_out/r2_launches_bench_summary.txt; head -16 gpurun_out/r2_launches_bench_summary.txt
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k "regex:dw_tma|dw_planar" --csv --log-file gpurun_out/r2_dw_traffic.csv $B > gpurun_out/r2_dw_traffic.log 2>&1
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv -lms 200 > gpurun_out/r2_clocks.csv &
 SMI=$!
 timeout 1200 python bench.py 2> gpurun_out/r2_bench_stderr.log | tail -1 > gpurun_out/r2_bench_m256x10_n1.json

@@ -390,6 +390,12 @@ static Plan make_plan(int H, int W, int Cs, int stride) {
   pl.LW = Wo > 16 ? 32 : (Wo > 8 ? 16 : 8);
   pl.Q = pl.LW == 32 ? 8 : (pl.LW == 16 ? 8 : 2);
   if (pl.LW == 16 && Ho <= 8) pl.Q = 4;
+  if (stride == 1 && pl.LW >= 16 && Ho > 8) {
+    // 8 or 7 output rows per thread, whichever pads the height less (56, 28, 14 rows: 7)
+    const int th8 = (32 / pl.LW) * 8, th7 = (32 / pl.LW) * 7;
+    const int pad8 = (Ho + th8 - 1) / th8 * th8, pad7 = (Ho + th7 - 1) / th7 * th7;
+    pl.Q = pad7 < pad8 ? 7 : 8;
+  }
   // stride 2: the halo tile (and with it the fp32 planar ring) is four times the output tile; two output
   // rows per thread keep two CTAs resident per SM
   if (stride == 2) pl.Q = 2;
@@ -497,7 +503,7 @@ extern "C" int x3d_dw3x3x3_planar_fwd(const void* in, const float* taps, void* o
 #define X3D_DWP(SS, LWW, QQ) \
   if (stride == SS && pl.LW == LWW && pl.Q == QQ) \
     return act ? dwp::launch<SS, LWW, QQ, true>(ti, to, p, N, pl, st) : dwp::launch<SS, LWW, QQ, false>(ti, to, p, N, pl, st)
-  X3D_DWP(1, 32, 8); X3D_DWP(1, 16, 8); X3D_DWP(1, 16, 4); X3D_DWP(1, 8, 2);
+  X3D_DWP(1, 32, 8); X3D_DWP(1, 16, 8); X3D_DWP(1, 32, 7); X3D_DWP(1, 16, 7); X3D_DWP(1, 16, 4); X3D_DWP(1, 8, 2);
   X3D_DWP(2, 32, 2); X3D_DWP(2, 16, 2); X3D_DWP(2, 8, 2);
 #undef X3D_DWP
   set_error("x3d_dw3x3x3_planar_fwd: no kernel for stride=%d LW=%d Q=%d", stride, pl.LW, pl.Q);

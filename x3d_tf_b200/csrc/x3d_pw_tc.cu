@@ -158,7 +158,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
     prefetch_tmap(&tmD);
-    if (p.a2_ppf) prefetch_tmap(&tmA2);
+    if (p.KC > p.KC1) prefetch_tmap(&tmA2);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -219,7 +219,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], kStageBytes);
           if (kc < p.KC1) tma_load_2d(sA + s * kStageBytes, &tmA, kc * kBlockK, row0, &full[s]);
-          else tma_load_4d(smem_u32(sA + s * kStageBytes), &tmA2, (kc - p.KC1) * kBlockK, 0, ho0, nt0, &full[s]);
+          else if (p.a2_ppf) tma_load_4d(smem_u32(sA + s * kStageBytes), &tmA2, (kc - p.KC1) * kBlockK, 0, ho0, nt0, &full[s]);
+          else tma_load_2d(sA + s * kStageBytes, &tmA2, (kc - p.KC1) * kBlockK, row0, &full[s]);   // dense [M, K2] rows
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -607,14 +608,16 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   if (a->A2) {
     // second source: its K2 channels continue the K loop at column KC1*64 of the packed weight
     X3D_REQUIRE(!a->R, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: A2 (shortcut as extra K) and R (residual) exclude each other");
-    X3D_REQUIRE(a->K2 > 0 && a->K2 % 8 == 0 && a->a2_stride >= 1 && a->a2_hi > 0 && a->a2_wi > 0 && a->a2_nt > 0,
-                X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: bad second source K2=%d stride=%d %dx%d", a->K2, a->a2_stride, a->a2_hi, a->a2_wi);
+    X3D_REQUIRE(a->K2 > 0 && a->K2 % 8 == 0 && a->a2_stride >= 0, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: bad second source K2=%d stride=%d", a->K2, a->a2_stride);
     X3D_REQUIRE((reinterpret_cast<uintptr_t>(a->A2) & 15) == 0, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: A2 must be 16-byte aligned");
-    a2_ho = (a->a2_hi - 1) / a->a2_stride + 1; a2_wo = (a->a2_wi - 1) / a->a2_stride + 1;
-    X3D_REQUIRE(a->M == a->a2_nt * a2_ho * a2_wo, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: M=%ld is not nt*Ho*Wo = %ld*%d*%d",
-                (long)a->M, (long)a->a2_nt, a2_ho, a2_wo);
-    X3D_REQUIRE(tc::sampler_box(a2_ho, a2_wo, &a2_bh, &a2_bf), X3D_ERR_UNSUPPORTED,
-                "x3d_pw_tc_fwd: 128-pixel tiles do not align with %dx%d frames (x3d_pw_tc_sampler_supported)", a2_ho, a2_wo);
+    if (a->a2_stride > 0) {
+      X3D_REQUIRE(a->a2_hi > 0 && a->a2_wi > 0 && a->a2_nt > 0, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: bad second source %dx%d", a->a2_hi, a->a2_wi);
+      a2_ho = (a->a2_hi - 1) / a->a2_stride + 1; a2_wo = (a->a2_wi - 1) / a->a2_stride + 1;
+      X3D_REQUIRE(a->M == a->a2_nt * a2_ho * a2_wo, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: M=%ld is not nt*Ho*Wo = %ld*%d*%d",
+                  (long)a->M, (long)a->a2_nt, a2_ho, a2_wo);
+      X3D_REQUIRE(tc::sampler_box(a2_ho, a2_wo, &a2_bh, &a2_bf), X3D_ERR_UNSUPPORTED,
+                  "x3d_pw_tc_fwd: 128-pixel tiles do not align with %dx%d frames (x3d_pw_tc_sampler_supported)", a2_ho, a2_wo);
+    }
     const int k16_2 = (a->K2 + 15) / 16, KC2 = (k16_2 + 3) / 4;
     KC = KC1 + KC2; k16_last = k16_2 - (KC2 - 1) * 4;
     X3D_REQUIRE(a->Kpad >= KC * 64, X3D_ERR_INVALID_ARG, "x3d_pw_tc_fwd: Kpad=%d < %d (both sources, 64-wide chunks)", a->Kpad, KC * 64);
@@ -651,14 +654,17 @@ extern "C" int x3d_pw_tc_fwd(const x3d_pw_tc_args* a, void* stream) {
   X3D_REQUIRE(tc::make_map_2d(&tmD, a->D, (uint64_t)a->Nc, (uint64_t)a->M, (uint64_t)a->ldd * 2, 64, 128),
               X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: tensor map for D failed (Nc=%d M=%ld ldd=%d)", a->Nc, (long)a->M, a->ldd);
   CUtensorMap tmA2 = tmA;
-  if (a->A2)
+  if (a->A2 && a->a2_stride > 0)
     X3D_REQUIRE(tc::make_map_sampler(&tmA2, a->A2, a->K2, a->a2_hi, a->a2_wi, (long)a->a2_nt, a->a2_stride, a2_wo, a2_bh, a2_bf),
                 X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: tensor map for A2 failed (K2=%d %dx%d stride %d)", a->K2, a->a2_hi, a->a2_wi, a->a2_stride);
+  else if (a->A2)
+    X3D_REQUIRE(tc::make_map_2d(&tmA2, a->A2, (uint64_t)a->K2, (uint64_t)a->M, (uint64_t)a->K2 * 2, 64, 128),
+                X3D_ERR_LAUNCH, "x3d_pw_tc_fwd: tensor map for dense A2 failed (K2=%d M=%ld)", a->K2, (long)a->M);
   tc::Params p;
   p.bias = a->bias; p.R = static_cast<const bf16*>(a->R); p.se = a->se; p.D = static_cast<bf16*>(a->D);
   p.M = a->M; p.rows_per_clip = a->rows_per_clip; p.Kc = a->K; p.Nc = a->Nc; p.ldr = a->ldr; p.ldd = a->ldd;
   p.colmean = a->colmean; p.ldc = a->Nc; p.store_d = a->colmean == nullptr || a->store_d;
-  p.KC1 = KC1; p.k16_last1 = k16_last1; p.a2_ppf = a->A2 ? a2_ho * a2_wo : 0; p.a2_wo = a2_wo;
+  p.KC1 = KC1; p.k16_last1 = k16_last1; p.a2_ppf = (a->A2 && a->a2_stride > 0) ? a2_ho * a2_wo : 0; p.a2_wo = a2_wo;
   p.NT = NT; p.KC = KC; p.k16_last = k16_last; p.stages = stages; p.tmem_cols = tmem_cols;
   p.relu = a->relu; p.swish = a->swish;
   p.contiguous = a->se != nullptr ? 1 : 0;

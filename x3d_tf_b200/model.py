@@ -330,8 +330,8 @@ class Options:
     pool_in_conv5 = os.environ.get("X3D_POOL_IN_CONV5", "1") == "1"
     # channelwise 3x3x3 kernel for bf16 activations: "tma" = x3d_dw3x3x3_act_fwd (thread = channel pair,
     # csrc/x3d_dw_tma.cu) everywhere; "auto" = the planar kernel (lanes = pixels, taps in uniform
-    # registers, csrc/x3d_dw_planar.cu) for the stride-1 layers wider than 8 pixels that fill >= 90 % of
-    # its lane grid (all of them at 256^2, none at 224^2 / 182^2), where it measures 5-13 % faster
+    # registers, csrc/x3d_dw_planar.cu) for the stride-1 layers wider than 8 pixels that fill >= 85 % of
+    # its lane grid (all of them at 256^2, the 56/28/14-wide ones at 224^2), where it measures 5-13 % faster
     # (profiles/r02_dw_planar.md); "planar" = wherever it has a plan.
     channelwise = os.environ.get("X3D_CHANNELWISE", "auto")
     # pointwise convs whose rows are not a multiple of 32 bytes (24 / 56 channels): two pixels per GEMM
@@ -492,7 +492,8 @@ class Bottleneck(Layer):
         return self._dev[key]
 
     def _forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None,
-                 relu: bool = False, shortcut: Optional[PointwiseConv] = None) -> torch.Tensor:
+                 relu: bool = False, shortcut: Optional[PointwiseConv] = None,
+                 shortcut_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x: [N,T,H,W,pad8(cin)].  `residual`/`relu`: the ResBlock add + ReLU fused into c's epilogue;
         `shortcut`: ResBlock's strided conv + bn_r, run on x as extra K columns of c (then no `residual`)."""
         if self.in_channels is None:
@@ -528,7 +529,7 @@ class Bottleneck(Layer):
             planar = a.dtype == torch.bfloat16 and cw != "tma" and \
                 ops.dw_planar_supported(T, H, W, ci, self.stride) > 0 and \
                 (cw == "planar" or (self.stride == 1 and W > 8 and
-                                    ops.dw_planar_lane_use(T, H, W, ci, self.stride) >= 0.9))
+                                    ops.dw_planar_lane_use(T, H, W, ci, self.stride) >= 0.85))
             if planar:
                 b, partial = ops.dw_planar_fwd(a, d["wbp"], self.stride, ph, pw, self.has_se, swish=swish_in_b)
             else:
@@ -541,7 +542,8 @@ class Bottleneck(Layer):
             se = ops.se_mlp_fwd(partial, T * Ho * Wo, d["w1"], d["b1"], d["w2"], d["b2"])
         ops.Profiler.tag = "c"
         if shortcut is not None:
-            out = d["c"].run_with_shortcut(b, N * T * Ho * Wo, shortcut, x, self.stride, se=se,
+            out = d["c"].run_with_shortcut(b, N * T * Ho * Wo, shortcut, x if shortcut_rows is None else shortcut_rows,
+                                           self.stride, se=se,
                                            rows_per_clip=T * Ho * Wo, swish=not swish_in_b, relu=relu)
         else:
             out = d["c"].run(b, N * T * Ho * Wo, use_tc=tc, se=se, rows_per_clip=T * Ho * Wo,
@@ -596,9 +598,12 @@ class ResBlock(Layer):
             s = self.stride
             Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
             ops.Profiler.tag = "shortcut"
-            if _use_tc() and x.dtype == torch.bfloat16 and Options.fold_shortcut and \
-                    ops.pw_tc_sampler_supported(H, W, s):
-                return self.bottleneck._forward(x, relu=True, shortcut=d["r"])
+            if _use_tc() and x.dtype == torch.bfloat16 and Options.fold_shortcut:
+                # the shortcut conv as extra K columns of the projection GEMM: sampled by TMA straight from
+                # x where 128-pixel tiles align with the output frames, else from the gathered rows
+                rows = None if ops.pw_tc_sampler_supported(H, W, s) else \
+                    (x.view(-1, x.shape[-1]) if s == 1 else ops.gather_rows_fwd(x, s))
+                return self.bottleneck._forward(x, relu=True, shortcut=d["r"], shortcut_rows=rows)
             if _use_tc() and x.dtype == torch.bfloat16:
                 # sampled pixels -> dense matrix -> tensor-core GEMM (bn_r folded)
                 rows = x.view(-1, x.shape[-1]) if s == 1 else ops.gather_rows_fwd(x, s)

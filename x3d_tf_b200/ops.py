@@ -195,7 +195,8 @@ def pw_tc_fwd(a: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], *
               relu: bool = False, a2: Optional[torch.Tensor] = None, a2_stride: int = 1,
               colmean: bool = False, store: bool = True):
     """tcgen05 pointwise GEMM (bf16).  `wp` is the packed [Npad, Kpad] bf16 weight.
-    `a2` [N,T,Hi,Wi,K2]: second K source sampled at (t, s*ho, s*wo) -- the shortcut conv folded in.
+    `a2` [N,T,Hi,Wi,K2]: second K source sampled at (t, s*ho, s*wo) -- the shortcut conv folded in;
+    or an already gathered dense [M,K2] matrix.
     `colmean`: also return the fp32 means over 64-row groups [2*ceil(M/128), Nc] (conv_5 + pool_5);
     with `store=False` the GEMM output itself is not written and only the means are returned."""
     _req(a, "a")
@@ -218,10 +219,15 @@ def pw_tc_fwd(a: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], *
     args.swish, args.relu = int(swish), int(relu)
     if a2 is not None:
         _req(a2, "a2")
-        if a2.dtype != torch.bfloat16 or a2.dim() != 5:
-            raise TypeError("pw_tc_fwd: a2 must be a bf16 [N,T,H,W,C] tensor")
-        args.A2, args.a2_nt, args.K2 = a2.data_ptr(), a2.shape[0] * a2.shape[1], a2.shape[4]
-        args.a2_stride, args.a2_hi, args.a2_wi = a2_stride, a2.shape[2], a2.shape[3]
+        if a2.dtype != torch.bfloat16 or a2.dim() not in (2, 5):
+            raise TypeError("pw_tc_fwd: a2 must be a bf16 [N,T,H,W,C] tensor or a dense [M,C] matrix")
+        if a2.dim() == 5:
+            args.A2, args.a2_nt, args.K2 = a2.data_ptr(), a2.shape[0] * a2.shape[1], a2.shape[4]
+            args.a2_stride, args.a2_hi, args.a2_wi = a2_stride, a2.shape[2], a2.shape[3]
+        else:
+            if a2.shape[0] != M:
+                raise ValueError("pw_tc_fwd: dense a2 needs M rows")
+            args.A2, args.K2, args.a2_stride = a2.data_ptr(), a2.shape[1], 0
     _launch("x3d_pw_tc_fwd", lambda: lib().x3d_pw_tc_fwd(args, _stream()))
     if colmean:
         return (out, means) if store else means
