@@ -30,11 +30,27 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().x3d_version() == 100
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """Every field of the argument structs sits where a C compiler puts it: a probe that includes
+    include/x3d_b200.h is compiled with gcc and its offsetof / sizeof are compared with ctypes."""
+    import subprocess
     from x3d_tf_b200 import _lib
-    # 6 pointers + int64 + 6 int32 + int64 + 11 int32 (padded to 8)
-    assert ctypes.sizeof(_lib.PwArgs) == 6 * 8 + 8 + 6 * 4 + 8 + 11 * 4 + 4
-    assert ctypes.sizeof(_lib.PwTcArgs) == 6 * 8 + 8 + 7 * 4 + 4 + 8 + 2 * 4
+    structs = {"x3d_pw_args": _lib.PwArgs, "x3d_pw_tc_args": _lib.PwTcArgs}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "x3d_b200.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
     assert _lib.PwArgs.rows_per_clip.offset == 80 and _lib.PwTcArgs.rows_per_clip.offset == 88
 
 
