@@ -50,8 +50,11 @@ __global__ void __launch_bounds__(256, MODE == 3 ? 2 : 3) ur_stencil(float* out,
    for (int u = 0; u < 3; ++u) {
     const int s = s3 + u;
     if (MODE == 4) {
+      unsigned long long ca;
+      asm("cvta.to.const.u64 %0, %1;" : "=l"(ca) : "l"((unsigned long long)(c_w + pl * 28)));
 #pragma unroll
-      for (int i = 0; i < 27; ++i) wv[i] = c_w[((pl + s) & 7) * 28 + i];
+      for (int i = 0; i < 27; ++i)
+        asm volatile("ld.const.v2.f32 {%0, %1}, [%2];" : "=f"(wv[i].x), "=f"(wv[i].y) : "l"(ca + i * 8u));
     }
 #pragma unroll
     for (int rr = 0; rr < RB; ++rr) {
