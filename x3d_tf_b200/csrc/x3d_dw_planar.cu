@@ -65,28 +65,29 @@ __device__ __forceinline__ void sts2_f32(uint32_t a, float lo, float hi) {
 __device__ __forceinline__ void sts_b32(uint32_t a, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
-// Barrier wait with an explicit back-off.  The hardware-suspended form (try_wait + time hint) wakes
-// on every barrier event of the CTA -- with 16 warps handing frames around that was one poll per
-// ~50 ns and warp, and the polling took half of the issue slots (profiles/r02_dw_planar.md).  Here:
-// one non-blocking test, then sleep `NS` ns between tests.  A lost arrival traps instead of hanging.
+// Barrier wait: hardware-suspended try_wait (the thread sleeps until the barrier's phase completes or the
+// time hint expires), retried; a lost arrival traps instead of hanging.  An earlier form slept with
+// `nanosleep` between non-blocking tests to save the issue slots of the polling helper warps: equal speed on
+// one box, but THREE TIMES slower on another B200 box of the same pool (stage-2 layer 0.45 -> 1.34 ms), where
+// the sleep evidently lasts far longer than asked -- nanosleep's duration is only bounded by 2x the argument
+// on top of the timer's resolution.  Nothing in this kernel may depend on a timer.
 template <int NS>
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra.uni DONE_%=;\n\t"
       "mov.u32 n, 0;\n"
       "SPIN_%=:\n\t"
-      "nanosleep.u32 %2;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra.uni DONE_%=;\n\t"
       "add.u32 n, n, 1;\n\t"
       "setp.lt.u32 q, n, %3;\n\t"
       "@q bra.uni SPIN_%=;\n\t"
       "trap;\n"
       "DONE_%=:\n\t}"
-      ::"r"(addr), "r"(parity), "n"(NS), "r"(1u << 24)
+      ::"r"(addr), "r"(parity), "r"(2000u), "r"(1u << 23)
       : "memory");
 }
 constexpr int kNsLane = 200, kNsXf = 100, kNsStencil = 0;   // producer / converter lanes, transposers, stencil
