@@ -7,7 +7,7 @@
 
 A "step" = one forward pass over one batch of synthetic clips of the workload's shape
 (default workload: BASELINE.json configs[2], X3D-M 10-view eval at 16x256x256, bf16,
-8 videos = 80 clips per GPU per step).  Prints ONE JSON line on rank 0; its headline fields are
+12 videos = 120 clips per GPU per step).  Prints ONE JSON line on rank 0; its headline fields are
 the m256x10 workload, and `configs` carries the other BASELINE configs (X3D-S 13x182^2, X3D-M
 16x224^2, X3D-L 16x356^2 forward; the X3D-M training step) measured in the same run, >= 10 timed
 steps each, at the same number of ranks.
@@ -32,7 +32,9 @@ WORKLOADS = {
     # name: (variant, T, S, views, default clips/GPU/step, dtype)
     "xs160": ("X3D_XS", 4, 160, 1, 8, "float32"),          # BASELINE configs[0]
     "s182": ("X3D_S", 13, 182, 1, 64, "bfloat16"),          # configs[1]
-    "m256x10": ("X3D_M", 16, 256, 10, 80, "bfloat16"),      # configs[2]  (metric config)
+    # 12 videos per step: measured 7503 / 7982 / 8157 / 8300 / 8462 / 8488 clips/s at 40 / 60 / 80 / 100 / 120 / 160
+    # clips per step (fixed per-launch costs of the 97 kernels; BASELINE configs[2] does not fix the batch)
+    "m256x10": ("X3D_M", 16, 256, 10, 120, "bfloat16"),     # configs[2]  (metric config)
     "m224": ("X3D_M", 16, 224, 1, 64, "bfloat16"),          # north_star target shape
     "l356": ("X3D_L", 16, 356, 1, 32, "bfloat16"),          # configs[3]
     "train_m224": ("X3D_M", 16, 224, 1, 32, "float32"),     # configs[4]: one training step
