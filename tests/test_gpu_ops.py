@@ -113,7 +113,8 @@ def test_channelwise(dtype, N, T, H, W, C, stride):
 
 @pytest.mark.parametrize("N,T,H,W,C,stride", DW_CASES + [(3, 4, 64, 64, 56, 1), (2, 16, 33, 70, 24, 1), (2, 5, 64, 64, 56, 2),
                                                         (5, 3, 8, 8, 432, 1), (2, 7, 16, 16, 216, 2), (2, 4, 56, 56, 56, 1),
-                                                        (3, 5, 28, 28, 112, 1), (3, 6, 14, 14, 216, 1)])   # 7 rows per thread
+                                                        (3, 5, 28, 28, 112, 1), (3, 6, 14, 14, 216, 1),   # 7 rows per thread
+                                                        (4, 6, 7, 7, 216, 1), (9, 4, 8, 6, 56, 1), (1, 3, 5, 8, 24, 1)])   # four clips per item
 def test_channelwise_planar(N, T, H, W, C, stride):
     """x3d_dw3x3x3_planar_fwd (lanes = pixels, taps in uniform registers) against the same oracle as
     x3d_dw3x3x3_fwd: output, SE partial sums, swish epilogue; several clips / tiles / chunks per CTA."""

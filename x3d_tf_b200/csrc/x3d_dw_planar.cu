@@ -101,34 +101,47 @@ struct Params {
   int act;               // 1: swish applied to the output
 };
 
-template <int S, int LW, int Q>
+// MC = clips per item.  MC = 1: the 32 / LW row strips of a warp are consecutive rows of ONE frame tile.
+// MC > 1 (= 32 / LW; frames no larger than LW x Q): every strip is a different CLIP, each with its own
+// halo block, so that a warp still has 32 busy lanes and Q rows per thread on 8x8 frames.
+template <int S, int LW, int Q, int MC>
 struct Geo {
   static constexpr int LS = 32 / LW;                 // row strips per warp
-  static constexpr int TH = LS * Q;                  // output rows per tile
+  static_assert(MC == 1 || MC == LS, "one clip per strip");
+  static constexpr int TH = MC > 1 ? Q : LS * Q;     // output rows per (clip's) tile
   static constexpr int BW = (LW - 1) * S + 3;        // halo tile
   static constexpr int BH = (TH - 1) * S + 3;
   static constexpr int RB = (Q - 1) * S + 3;         // input rows one thread touches
-  static constexpr int raw_bytes = (BH * BW * kCh * 2 + 127) / 128 * 128;
-  static constexpr int plane_bytes = BH * BW * 8 + 16;      // fp32 pairs; +16: planes 4 apart land on other banks
+  static constexpr int raw_clip = BH * BW * kCh * 2; // one TMA box
+  static constexpr int raw_bytes = (MC * raw_clip + 127) / 128 * 128;
+  // fp32 pairs of one clip's halo block; with MC > 1 the blocks are padded so that neighbouring strips sit
+  // 16 banks apart (a half-warp = two strips reads 2 x 64 bytes)
+  static constexpr int blk_px = BH * BW;
+  static constexpr int blk_bytes = MC > 1 ? (blk_px * 2 + (48 - blk_px * 2 % 32) % 32) * 4 : blk_px * 8;
+  static constexpr int plane_bytes = MC * blk_bytes + 16;   // +16: planes 4 apart land on other banks
   static constexpr int ring_bytes = (kPairs * plane_bytes + 127) / 128 * 128;
-  static constexpr int stage_bytes = TH * LW * kCh * 2;     // dense [TH][LW][16] bf16: TMA store box
-  // planar output frame: [pair][TH*LW] bf16x2 words; +4 words: planes 4 apart sit 16 banks apart, so the
-  // converter's two lanes per pixel (pairs j and j+4) never collide
-  static constexpr int oplane_bytes = (TH * LW + 4) * 4;
+  static constexpr int stage_clip = TH * LW * kCh * 2;      // dense [TH][LW][16] bf16: one TMA store box
+  static constexpr int stage_bytes = MC * stage_clip;
+  // planar output frame: [pair][MC][TH*LW] bf16x2 words; +4 words: planes 4 apart sit 16 banks apart, so the
+  // converter's two lanes per pixel (pairs j and j+4) never collide; with MC > 1 a clip's block is padded by
+  // 8 words so that the four strips of a warp store to different banks
+  static constexpr int oblk_bytes = MC > 1 ? (TH * LW + 8) * 4 : TH * LW * 4;
+  static constexpr int oplane_bytes = MC * oblk_bytes + 16;
   static constexpr int pout_bytes = (kPairs * oplane_bytes + 127) / 128 * 128;
   static constexpr int off_raw = 256;
   static constexpr int off_ring = off_raw + kRaw * raw_bytes;
   static constexpr int off_pout = off_ring + kRing * ring_bytes;
   static constexpr int off_stage = off_pout + kOut * pout_bytes;
-  static constexpr int smem = off_stage + 2 * stage_bytes + 128;
+  static constexpr int kStage = MC > 1 ? 1 : 2;             // NDHWC tiles (MC > 1: one, for the shared-memory budget)
+  static constexpr int smem = off_stage + kStage * stage_bytes + 128;
   static_assert(smem <= 113 * 1024, "two CTAs per SM");
 };
 
-template <int S, int LW, int Q, bool ACT>
+template <int S, int LW, int Q, bool ACT, int MC>
 __global__ void __launch_bounds__(kThreads, 2)
 dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
                  const Params p) {
-  using G = Geo<S, LW, Q>;
+  using G = Geo<S, LW, Q, MC>;
   extern __shared__ __align__(128) uint8_t dwp_smem_raw[];
   const uint32_t raw_a = smem_u32(dwp_smem_raw);
   const uint32_t smem_s = (raw_a + 127u) & ~127u;
@@ -146,7 +159,7 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int total = p.N * p.tiles * p.chunks;
+  const int total = ((p.N + MC - 1) / MC) * p.tiles * p.chunks;        // items: (clip group, tile, chunk)
 
   if (tid == 0) {
     prefetch_tmap(&tmIn);
@@ -168,6 +181,7 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     const int r = idx / p.chunks;
     n = r / p.tiles;
     tile = r - n * p.tiles;
+    n *= MC;                                            // first clip of the item
     const int th = tile / p.tiles_w;
     ho0 = th * G::TH;
     wo0 = (tile - th * p.tiles_w) * LW;
@@ -185,8 +199,11 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
         const int hi0 = ho0 * S - p.pad_h, wi0 = wo0 * S - p.pad_w;
         for (int f = 0; f < p.T; ++f) {
           mbar_wait_sleep<kNsLane>(&raw_empty[s], ph ^ 1u);
-          mbar_expect_tx(&raw_full[s], static_cast<uint32_t>(G::BH * G::BW * kCh * 2));
-          tma_load_5d(rawb_s + s * G::raw_bytes, &tmIn, chunk * kCh, wi0, hi0, f, n, &raw_full[s]);
+          // (a clip index past N is out of the tensor: the box arrives as zeros and still counts its bytes)
+          mbar_expect_tx(&raw_full[s], static_cast<uint32_t>(MC * G::raw_clip));
+#pragma unroll
+          for (int c = 0; c < MC; ++c)
+            tma_load_5d(rawb_s + s * G::raw_bytes + c * G::raw_clip, &tmIn, chunk * kCh, wi0, hi0, f, n + c, &raw_full[s]);
           if (++s == kRaw) { s = 0; ph ^= 1u; }
         }
       }
@@ -197,8 +214,9 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     // unit = (pixel, half): lane reads the bf16x2 words of 4 channel pairs at one pixel and writes them
     // as 16 contiguous bytes of the NDHWC tile.  Two NDHWC tiles alternate; a tile is rewritten once
     // the bulk store issued from it two frames ago has read it (wait_group.read 1).
-    constexpr int kOUnits = G::TH * LW * 2;
+    constexpr int kOUnits = MC * G::TH * LW * 2;
     static_assert(kOUnits % 32 == 0, "whole warps of units");
+    static_assert(MC == 1 || (G::TH * LW) % 16 == 0, "a warp round of 16 pixels stays inside one clip");
     const uint32_t lsrc = static_cast<uint32_t>((lane & 1) * 4) * G::oplane_bytes + static_cast<uint32_t>(lane >> 1) * 4;
     const uint32_t ldst = static_cast<uint32_t>(lane) * 16;
     int k = 0, j = 0;
@@ -207,13 +225,14 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
       int n, tile, chunk, ho0, wo0;
       decode(idx, n, tile, chunk, ho0, wo0);
       for (int f = 0; f < p.T; ++f) {
-        if (lane == 0) tma_store_wait_read<1>();
+        if (lane == 0) tma_store_wait_read<G::kStage - 1>();
         mbar_wait_sleep<kNsXf>(&out_full[k], kph);
         __syncwarp();
         const uint32_t src = pout_s + k * G::pout_bytes + lsrc, dst = stage_s + j * G::stage_bytes + ldst;
 #pragma unroll 4
         for (int i = 0; i < kOUnits / 32; ++i) {
-          const uint32_t a = src + i * 64;                   // 16 pixels per warp round
+          // 16 pixels per warp round; with MC > 1 the clips' blocks of the planar frame are padded
+          const uint32_t a = src + (MC > 1 ? (i * 16 / (G::TH * LW)) * G::oblk_bytes + (i * 16 % (G::TH * LW)) * 4 : i * 64);
           uint32_t w0, w1, w2, w3;
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(a));
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(a + G::oplane_bytes));
@@ -225,10 +244,12 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&out_empty[k]);
-          tma_store_5d(&tmOut, stage_s + j * G::stage_bytes, chunk * kCh, wo0, ho0, f, n);
+#pragma unroll
+          for (int c = 0; c < MC; ++c)                        // (a clip past N: the whole box is clipped)
+            tma_store_5d(&tmOut, stage_s + j * G::stage_bytes + c * G::stage_clip, chunk * kCh, wo0, ho0, f, n + c);
           tma_store_commit();
         }
-        j ^= 1;
+        if (G::kStage > 1) j ^= 1;
         if (++k == kOut) { k = 0; kph ^= 1u; }
       }
     }
@@ -239,7 +260,7 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     // one fp32 pair at [pair][pixel]
     reg_dec<kRegsHelper>();
     const int tt = tid - kXfWarp0 * 32;
-    constexpr int kUnits = G::BH * G::BW * 2;
+    constexpr int kUnits = MC * G::blk_px * 2;
     int s = 0, r = 0;
     uint32_t sph = 0, rph = 0;
     for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
@@ -251,7 +272,10 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
         for (int u = tt; u < kUnits; u += kXfWarps * 32) {
           uint32_t w0, w1, w2, w3;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(src + u * 16));
-          const uint32_t d = dst + static_cast<uint32_t>((u & 1) * 4) * G::plane_bytes + static_cast<uint32_t>(u >> 1) * 8;
+          const int px = u >> 1;
+          const uint32_t d = dst + static_cast<uint32_t>((u & 1) * 4) * G::plane_bytes +
+                             (MC > 1 ? static_cast<uint32_t>(px / G::blk_px) * G::blk_bytes + static_cast<uint32_t>(px % G::blk_px) * 8
+                                     : static_cast<uint32_t>(px) * 8);
           sts2_f32(d, __uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u));
           sts2_f32(d + G::plane_bytes, __uint_as_float(w1 << 16), __uint_as_float(w1 & 0xffff0000u));
           sts2_f32(d + 2 * G::plane_bytes, __uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u));
@@ -274,8 +298,11 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     const int pl = __shfl_sync(0xffffffffu, warp - kStWarp0, 0);       // plane (pair inside the chunk)
     const int col = lane % LW, strip = lane / LW;
     const uint32_t toff = static_cast<uint32_t>(pl) * G::plane_bytes +
-                          static_cast<uint32_t>((strip * Q * S) * G::BW + col * S) * 8;
-    const uint32_t soff = static_cast<uint32_t>(pl) * G::oplane_bytes + static_cast<uint32_t>((strip * Q) * LW + col) * 4;
+                          (MC > 1 ? static_cast<uint32_t>(strip) * G::blk_bytes + static_cast<uint32_t>(col * S) * 8
+                                  : static_cast<uint32_t>((strip * Q * S) * G::BW + col * S) * 8);
+    const uint32_t soff = static_cast<uint32_t>(pl) * G::oplane_bytes +
+                          (MC > 1 ? static_cast<uint32_t>(strip) * G::oblk_bytes + static_cast<uint32_t>(col) * 4
+                                  : static_cast<uint32_t>((strip * Q) * LW + col) * 4);
     int r = 0, k = 0;
     uint32_t rph = 0, kph = 0;
 
@@ -290,7 +317,8 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
       for (int i = 0; i < 27; ++i) wv[i] = tp[i];
       const float2 bia = tp[27];
       const bool col_ok = wo0 + col < p.Wo;
-      const int rows_ok = p.Ho - (ho0 + strip * Q);          // output rows of this thread inside the image
+      // output rows of this thread inside the image (MC > 1: the strip is its own clip, which may lie past N)
+      const int rows_ok = MC > 1 ? (n + strip < p.N ? p.Ho - ho0 : 0) : p.Ho - (ho0 + strip * Q);
 
       // The BN shift is added when a frame is emitted (FADD2 with the uniform operand), so a set is
       // (re)started by its first tap with a zero addend and the shift never has to sit in registers.
@@ -366,13 +394,15 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
       else emit_out(acc[1]);
 
       if (p.partial != nullptr) {
+        // MC = 1: the whole warp is one clip's tile; MC > 1: every LW lanes are a clip of their own
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = (MC > 1 ? LW / 2 : 16); o > 0; o >>= 1) {
           ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, o);
           ssum.y += __shfl_xor_sync(0xffffffffu, ssum.y, o);
         }
-        if (lane == 0 && chan) {
-          float* dstp = p.partial + (static_cast<long>(n) * p.tiles + tile) * p.Cs + 2 * pair;
+        const int nn = MC > 1 ? n + strip : n;
+        if ((MC > 1 ? col == 0 : lane == 0) && chan && nn < p.N) {
+          float* dstp = p.partial + (static_cast<long>(nn) * p.tiles + tile) * p.Cs + 2 * pair;
           dstp[0] = ssum.x;
           dstp[1] = ssum.y;
         }
@@ -382,7 +412,7 @@ dw_planar_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------ host
-struct Plan { int LW, Q, TH, tiles_w, tiles_h, chunks; size_t smem; };
+struct Plan { int LW, Q, TH, MC, tiles_w, tiles_h, chunks; size_t smem; };
 
 static Plan make_plan(int H, int W, int Cs, int stride) {
   const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
@@ -400,24 +430,27 @@ static Plan make_plan(int H, int W, int Cs, int stride) {
   // stride 2: the halo tile (and with it the fp32 planar ring) is four times the output tile; two output
   // rows per thread keep two CTAs resident per SM
   if (stride == 2) pl.Q = 2;
+  pl.MC = 1;
   pl.TH = (32 / pl.LW) * pl.Q;
+  // stride 1 on frames of at most 8x8 pixels: the four strips of a warp are four CLIPS, 8 rows per thread
+  if (stride == 1 && pl.LW == 8 && Ho <= 8) { pl.MC = 4; pl.Q = 8; pl.TH = 8; }
   pl.tiles_w = (Wo + pl.LW - 1) / pl.LW;
   pl.tiles_h = (Ho + pl.TH - 1) / pl.TH;
   pl.chunks = (Cs + kCh - 1) / kCh;
   return pl;
 }
 
-template <int S, int LW, int Q, bool ACT>
+template <int S, int LW, int Q, bool ACT, int MC = 1>
 static int launch(const CUtensorMap& ti, const CUtensorMap& to, const Params& p, int N, const Plan& pl, cudaStream_t st) {
-  using G = Geo<S, LW, Q>;
-  auto kern = dw_planar_kernel<S, LW, Q, ACT>;
+  using G = Geo<S, LW, Q, MC>;
+  auto kern = dw_planar_kernel<S, LW, Q, ACT, MC>;
   static SmemOptIn optin;
   const cudaError_t e = ensure_dynamic_smem(kern, optin, G::smem);
   if (e != cudaSuccess) {
     set_error("x3d_dw3x3x3_planar_fwd: smem attribute (%d B): %s", G::smem, cudaGetErrorString(e));
     return X3D_ERR_LAUNCH;
   }
-  const long total = (long)N * pl.tiles_w * pl.tiles_h * pl.chunks;
+  const long total = (long)((N + MC - 1) / MC) * pl.tiles_w * pl.tiles_h * pl.chunks;
   long gx = 2L * device_sm_count();
   if (gx > total) gx = total;
   const cudaError_t le = launch_pdl(kern, dim3((unsigned)gx), dim3(kThreads), G::smem, st, ti, to, p);
@@ -504,6 +537,8 @@ extern "C" int x3d_dw3x3x3_planar_fwd(const void* in, const float* taps, void* o
 #define X3D_DWP(SS, LWW, QQ) \
   if (stride == SS && pl.LW == LWW && pl.Q == QQ) \
     return act ? dwp::launch<SS, LWW, QQ, true>(ti, to, p, N, pl, st) : dwp::launch<SS, LWW, QQ, false>(ti, to, p, N, pl, st)
+  if (pl.MC == 4)
+    return act ? dwp::launch<1, 8, 8, true, 4>(ti, to, p, N, pl, st) : dwp::launch<1, 8, 8, false, 4>(ti, to, p, N, pl, st);
   X3D_DWP(1, 32, 8); X3D_DWP(1, 16, 8); X3D_DWP(1, 32, 7); X3D_DWP(1, 16, 7); X3D_DWP(1, 16, 4); X3D_DWP(1, 8, 2);
   X3D_DWP(2, 32, 2); X3D_DWP(2, 16, 2); X3D_DWP(2, 8, 2);
 #undef X3D_DWP

@@ -330,8 +330,8 @@ class Options:
     pool_in_conv5 = os.environ.get("X3D_POOL_IN_CONV5", "1") == "1"
     # channelwise 3x3x3 kernel for bf16 activations: "tma" = x3d_dw3x3x3_act_fwd (thread = channel pair,
     # csrc/x3d_dw_tma.cu) everywhere; "auto" = the planar kernel (lanes = pixels, taps in uniform
-    # registers, csrc/x3d_dw_planar.cu) for the stride-1 layers wider than 8 pixels that fill >= 85 % of
-    # its lane grid (all of them at 256^2, the 56/28/14-wide ones at 224^2), where it measures 5-13 % faster
+    # registers, csrc/x3d_dw_planar.cu) for the stride-1 layers that fill >= 85 % of its lane grid (all of
+    # them at 256^2 -- 8x8 frames four clips at a time --, the 28/14-wide ones at 224^2), where it measures 5-13 % faster
     # (profiles/r02_dw_planar.md); "planar" = wherever it has a plan.
     channelwise = os.environ.get("X3D_CHANNELWISE", "auto")
     # pointwise convs whose rows are not a multiple of 32 bytes (24 / 56 channels): two pixels per GEMM
@@ -528,7 +528,7 @@ class Bottleneck(Layer):
             cw = Options.channelwise
             planar = a.dtype == torch.bfloat16 and cw != "tma" and \
                 ops.dw_planar_supported(T, H, W, ci, self.stride) > 0 and \
-                (cw == "planar" or (self.stride == 1 and W > 8 and
+                (cw == "planar" or (self.stride == 1 and
                                     ops.dw_planar_lane_use(T, H, W, ci, self.stride) >= 0.85))
             if planar:
                 b, partial = ops.dw_planar_fwd(a, d["wbp"], self.stride, ph, pw, self.has_se, swish=swish_in_b)
