@@ -314,7 +314,7 @@ class Options:
     fuse_expand = os.environ.get("X3D_FUSE_EXPAND", "off")
     # uint8 clips in bf16 mode: "normalize" = x3d_normalize_u8 then the ordinary stem;
     # "fused" = x3d_stem_tc_u8_fwd (the stem's loader reads bytes through a lookup table)
-    stem_u8 = "normalize"
+    stem_u8 = os.environ.get("X3D_STEM_U8", "normalize")
     # blocks without SE: apply swish in the channelwise kernel's epilogue (x3d_dw3x3x3_act_fwd)
     # instead of the projection GEMM's prologue, which then runs without its transform warps.
     # Measured back to back at 80 clips of 16x256^2: c 2.83 -> 2.50 ms, b 4.97 -> 5.18 ms (the stencil
